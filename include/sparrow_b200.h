@@ -1,0 +1,132 @@
+/*
+ * sparrow_b200.h -- C ABI of the B200-native DirectionalRadiosityFast hot path.
+ *
+ * The reference (sparrow-acoustics/sparrowpy v1.0.1) has no FFI layer; its
+ * operator boundary is the set of numba-jitted array functions that the class
+ * methods call by name ("Seam B").  Every entry point below
+ * replaces one of those functions and cites it.  A maintainer binds them with
+ * ctypes.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions across the boundary;
+ *   - every pointer is a DEVICE pointer owned by the caller (e.g. a torch tensor's
+ *     data_ptr()) unless its name ends in _h (host); nothing is allocated behind
+ *     the caller's back -- scratch space is passed in explicitly;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*), no
+ *     implicit synchronisation;
+ *   - return value 0 = success, negative = error; spb_last_error() gives the
+ *     message of the calling thread's last failure;
+ *   - dtype: SPB_F64 = 0 (reference precision), SPB_F32 = 1 (histograms in fp32).
+ *
+ * Energy histogram layout in HBM ("padded rows"):
+ *   E[row][PAD + t],  row = (patch * D + direction) * B + band,
+ *   row stride LD = PAD + T_pad elements.  The PAD leading elements of every row
+ *   are a zero pre-roll (t < 0), PAD >= the largest pair delay, so a delayed read
+ *   E[row][PAD + t - delay] never needs a bounds test.  T_pad >= T is the tile
+ *   multiple the caller got from spb_exchange_layout().
+ */
+#ifndef SPARROW_B200_H
+#define SPARROW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_F64 0
+#define SPB_F32 1
+
+int spb_version(void);
+const char *spb_last_error(void);
+/* number of SMs / device name of the current device (sanity + grid sizing) */
+int spb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------
+ * Energy exchange (reference RadiosityFast.py:1037-1145, `_energy_exchange` and
+ * `_energy_exchange_init_energy`).
+ *
+ * Factored form of form_factors_tilde (RadiosityFast.py:1234-1272): a directed
+ * visible pair q = (sender i -> receiver j) carries
+ *     weight ff_q, delay bin dly_q, sender row src_q = i*D + out_dir(i,j),
+ *     class  c_q = brdf_index[wall(i)] * S + in_dir(i,j)
+ * and the dense tensor is tilde[i,j,d,b] = ff_q * coef[c_q, d, b] with
+ *     coef[c,d,b] = exp(-air[b]) * brdf[c,d,b].
+ * Pairs are stored receiver-major: segment s = c*N + j owns entries
+ * seg_ptr[s] .. seg_ptr[s+1].
+ *
+ * One reflection order = gather (stage 1) followed by mix (stage 2):
+ *     G[c,j,b,t]   = sum_{q in seg(c,j)} ff_q * E_prev[src_q, b, t - dly_q]
+ *     E_cur[j,d,b,t] = sum_c coef[c,d,b] * G[c,j,b,t];   E_total += E_cur
+ * ------------------------------------------------------------------------- */
+
+/* Tile geometry the kernels expect: T_pad (multiple of the time tile) and PAD
+ * (>= max_delay, multiple of 32).  LD = PAD + T_pad. */
+int spb_exchange_layout(int64_t n_samples, int64_t max_delay, int dtype,
+                        int64_t *t_pad, int64_t *pad);
+
+/* `_energy_exchange_init_energy` (RadiosityFast.py:1037-1070): zero e_total and
+ * e_prev, then add e0[i,d,b] at bin delay0[i] of every row of patch i.  Energy
+ * whose bin is >= n_samples is dropped (the reference writes out of bounds).
+ * e0: [N, D*B]; delay0: [N] int32; e_total/e_prev: [N*D*B, LD] (e_prev may be 0). */
+int spb_exchange_init(void *e_total, void *e_prev, const void *e0,
+                      const int32_t *delay0, int64_t n_patches, int64_t db,
+                      int64_t n_samples, int64_t ld, int64_t pad, int dtype,
+                      void *stream);
+
+/* Stage 1 of one order for receiver patches [j_lo, j_hi) (all of them on one
+ * GPU, a shard on several).  g: [C*N*B, LD], only rows of non-empty segments in
+ * the range are written.  seg_ptr: [C*N + 1] int64; src, dly: int32; wgt: dtype. */
+int spb_exchange_gather(const void *e_prev, void *g, const int64_t *seg_ptr,
+                        const int32_t *src, const void *wgt, const int32_t *dly,
+                        int64_t n_patches, int64_t n_classes, int64_t n_bands,
+                        int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
+                        int64_t pad, int dtype, void *stream);
+
+/* Stage 2 of one order for receiver patches [j_lo, j_hi): BRDF contraction,
+ * writes e_cur rows of those patches and accumulates them into e_total.
+ * coef: [C, D, B] in dtype. */
+int spb_exchange_mix(const void *g, void *e_cur, void *e_total,
+                     const int64_t *seg_ptr, const void *coef, int64_t n_patches,
+                     int64_t n_classes, int64_t n_dirs, int64_t n_bands,
+                     int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
+                     int64_t pad, int dtype, void *stream);
+
+/* `_energy_exchange` (RadiosityFast.py:1073-1145) on one GPU: init + max_order
+ * x (gather, mix).  e_a, e_b: ping-pong [N*D*B, LD]; g: [C*N*B, LD].
+ * max_order < 1 means "initial energy only" (RadiosityFast.py:550-555, :1119). */
+int spb_energy_exchange(const void *e0, const int32_t *delay0,
+                        const int64_t *seg_ptr, const int32_t *src, const void *wgt,
+                        const int32_t *dly, const void *coef, int64_t n_patches,
+                        int64_t n_classes, int64_t n_dirs, int64_t n_bands,
+                        int64_t n_samples, int64_t t_pad, int64_t pad,
+                        int64_t max_order, void *e_total, void *e_a, void *e_b,
+                        void *g, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Receiver collection (reference RadiosityFast.py:686-752 `_collect_energy_patches`
+ * + :1148-1185 `_collect_receiver_energy`):
+ *   out[r,b,(t + shift[r,k]) mod T] += e_total[k, rdir[r,k], b, t] * scale[r,k,b]
+ * scale = patch->receiver factor * exp(-air[b]*dist), shift = ceil-delay mod T
+ * (the reference's np.roll is circular).  mono: [R, B, T] dense (no padding).
+ * partial: scratch [n_split, R, B, T].
+ * ------------------------------------------------------------------------- */
+int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *shift,
+                     const void *scale, int64_t n_receivers, int64_t n_patches,
+                     int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
+                     int64_t pad, void *mono, void *partial, int64_t n_split,
+                     int dtype, void *stream);
+
+/* patch-wise variant (`collect_energy_receiver_patchwise`, RadiosityFast.py:660):
+ * out: [R, N, B, T] dense. */
+int spb_collect_patchwise(const void *e_total, const int32_t *rdir,
+                          const int32_t *shift, const void *scale,
+                          int64_t n_receivers, int64_t n_patches, int64_t n_dirs,
+                          int64_t n_bands, int64_t n_samples, int64_t ld, int64_t pad,
+                          void *out, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARROW_B200_H */

@@ -1,0 +1,401 @@
+// Energy exchange, initial energy and receiver collection kernels (sm_100a).
+//
+// Replaces the numba kernels `_energy_exchange_init_energy`, `_energy_exchange`
+// and `_collect_receiver_energy` (reference RadiosityFast.py:1037-1185).  See
+// include/sparrow_b200.h for the data layout and DESIGN.md for the roofline.
+#include "common.cuh"
+
+namespace spb {
+
+std::string &last_error() {
+    static thread_local std::string msg;
+    return msg;
+}
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kChunks = 8;                 // 32-bin chunks per lane
+constexpr int kTimeTile = 32 * kChunks;    // 256 time bins per warp
+
+// ---------------------------------------------------------------------------
+// initial energy: RadiosityFast.py:1037-1070
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void k_init_scatter(T *__restrict__ e_total, T *__restrict__ e_prev,
+                               const T *__restrict__ e0,
+                               const int32_t *__restrict__ delay0, int64_t n_rows,
+                               int64_t db, int64_t n_samples, int64_t ld, int64_t pad) {
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    int64_t patch = row / db;
+    int32_t d = delay0[patch];
+    if (d < 0 || d >= n_samples) return;   // out-of-range energy is dropped
+    T v = e0[row];
+    e_total[row * ld + pad + d] += v;
+    if (e_prev) e_prev[row * ld + pad + d] += v;
+}
+
+// ---------------------------------------------------------------------------
+// stage 1: sparse delay-and-sum  (RadiosityFast.py:1124-1143, one order)
+//   G[seg, b, t] = sum_q wgt_q * E_prev[src_q * B + b, t - dly_q]
+// one warp per (band, segment); lanes run along time, kChunks chunks of 32 bins
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_gather(const T *__restrict__ e_prev, T *__restrict__ g,
+         const int64_t *__restrict__ seg_ptr, const int32_t *__restrict__ src,
+         const T *__restrict__ wgt, const int32_t *__restrict__ dly,
+         int64_t n_patches, int64_t n_classes, int64_t n_bands, int64_t j_lo,
+         int64_t n_j, int64_t ld, int64_t pad) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t n_local = n_classes * n_j;
+    const int64_t widx = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    if (widx >= n_local * n_bands) return;
+    const int64_t b = widx / n_local;
+    const int64_t loc = widx - b * n_local;
+    const int64_t c = loc / n_j;
+    const int64_t seg = c * n_patches + j_lo + (loc - c * n_j);
+    const int64_t p0 = seg_ptr[seg], p1 = seg_ptr[seg + 1];
+    if (p0 == p1) return;                  // empty segment: row is never read
+    const int64_t t0 = (int64_t)blockIdx.y * kTimeTile;
+
+    T acc[kChunks];
+#pragma unroll
+    for (int v = 0; v < kChunks; ++v) acc[v] = T(0);
+    const T *base = e_prev + b * ld + pad + t0 + lane;
+    const int64_t row_stride = n_bands * ld;
+
+    for (int64_t p = p0; p < p1; p += 32) {
+        const int64_t q = p + lane;
+        int32_t s = 0, d = 0;
+        T w = T(0);
+        if (q < p1) { s = src[q]; w = wgt[q]; d = dly[q]; }
+        const int cnt = (int)min((int64_t)32, p1 - p);
+        for (int k = 0; k < cnt; ++k) {
+            const int32_t sk = __shfl_sync(0xffffffffu, s, k);
+            const int32_t dk = __shfl_sync(0xffffffffu, d, k);
+            const T wk = __shfl_sync(0xffffffffu, w, k);
+            const T *row = base + (int64_t)sk * row_stride - dk;
+#pragma unroll
+            for (int v = 0; v < kChunks; ++v) acc[v] = fma(wk, row[32 * v], acc[v]);
+        }
+    }
+    T *out = g + (seg * n_bands + b) * ld + pad + t0 + lane;
+#pragma unroll
+    for (int v = 0; v < kChunks; ++v) out[32 * v] = acc[v];
+}
+
+// ---------------------------------------------------------------------------
+// stage 2: BRDF contraction + accumulation
+//   E_cur[j,d,b,t] = sum_c coef[c,d,b] * G[c,j,b,t];  E_total += E_cur
+// one CTA per (patch, band, time slab); threads along time
+// ---------------------------------------------------------------------------
+constexpr int kMixDirs = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_mix(const T *__restrict__ g, T *__restrict__ e_cur, T *__restrict__ e_total,
+      const int64_t *__restrict__ seg_ptr, const T *__restrict__ coef,
+      int64_t n_patches, int64_t n_classes, int64_t n_dirs, int64_t n_bands,
+      int64_t j_lo, int64_t t_pad, int64_t ld, int64_t pad) {
+    const int64_t jb = blockIdx.x;
+    const int64_t j = j_lo + jb / n_bands;
+    const int64_t b = jb % n_bands;
+    const int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (t >= t_pad) return;
+    for (int64_t d0 = 0; d0 < n_dirs; d0 += kMixDirs) {
+        T acc[kMixDirs];
+#pragma unroll
+        for (int dd = 0; dd < kMixDirs; ++dd) acc[dd] = T(0);
+        for (int64_t c = 0; c < n_classes; ++c) {
+            const int64_t seg = c * n_patches + j;
+            if (seg_ptr[seg] == seg_ptr[seg + 1]) continue;   // CTA-uniform
+            const T gv = g[(seg * n_bands + b) * ld + pad + t];
+            const T *cf = coef + (c * n_dirs + d0) * n_bands + b;
+#pragma unroll
+            for (int dd = 0; dd < kMixDirs; ++dd)
+                if (d0 + dd < n_dirs) acc[dd] = fma(cf[dd * n_bands], gv, acc[dd]);
+        }
+#pragma unroll
+        for (int dd = 0; dd < kMixDirs; ++dd) {
+            if (d0 + dd < n_dirs) {
+                const int64_t o = ((j * n_dirs + d0 + dd) * n_bands + b) * ld + pad + t;
+                e_cur[o] = acc[dd];
+                e_total[o] += acc[dd];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// receiver collection: RadiosityFast.py:735-748, :1148-1185
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_collect_partial(const T *__restrict__ e_total, const int32_t *__restrict__ rdir,
+                  const int32_t *__restrict__ shift, const T *__restrict__ scale,
+                  int64_t n_patches, int64_t n_dirs, int64_t n_bands,
+                  int64_t n_samples, int64_t ld, int64_t pad, T *__restrict__ partial,
+                  int64_t n_split) {
+    const int64_t rb = blockIdx.y;             // receiver * B + band
+    const int64_t r = rb / n_bands, b = rb % n_bands;
+    const int64_t split = blockIdx.z;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // output bin
+    const int64_t k_lo = n_patches * split / n_split;
+    const int64_t k_hi = n_patches * (split + 1) / n_split;
+    T acc = T(0);
+    if (t < n_samples) {
+        for (int64_t k = k_lo; k < k_hi; ++k) {
+            const int64_t rk = r * n_patches + k;
+            const T sc = scale[rk * n_bands + b];
+            if (sc == T(0)) continue;          // invisible patch (CTA-uniform)
+            int64_t ts = t - shift[rk];
+            if (ts < 0) ts += n_samples;       // circular np.roll
+            acc += e_total[((k * n_dirs + rdir[rk]) * n_bands + b) * ld + pad + ts] * sc;
+        }
+        partial[((split * gridDim.y) + rb) * n_samples + t] = acc;
+    }
+}
+
+template <typename T>
+__global__ void k_collect_reduce(const T *__restrict__ partial, T *__restrict__ mono,
+                                 int64_t n_out, int64_t n_split) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    T acc = T(0);
+    for (int64_t s = 0; s < n_split; ++s) acc += partial[s * n_out + o];
+    mono[o] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_collect_patchwise(const T *__restrict__ e_total, const int32_t *__restrict__ rdir,
+                    const int32_t *__restrict__ shift, const T *__restrict__ scale,
+                    int64_t n_patches, int64_t n_dirs, int64_t n_bands,
+                    int64_t n_samples, int64_t ld, int64_t pad, T *__restrict__ out) {
+    const int64_t rkb = blockIdx.x;            // (receiver * N + patch) * B + band
+    const int64_t b = rkb % n_bands;
+    const int64_t rk = rkb / n_bands;
+    const int64_t k = rk % n_patches;
+    const int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (t >= n_samples) return;
+    int64_t ts = t - shift[rk];
+    if (ts < 0) ts += n_samples;
+    out[rkb * n_samples + t] =
+        e_total[((k * n_dirs + rdir[rk]) * n_bands + b) * ld + pad + ts] *
+        scale[rk * n_bands + b];
+}
+
+// ---------------------------------------------------------------------------
+// typed launchers
+// ---------------------------------------------------------------------------
+template <typename T>
+int init_t(void *e_total, void *e_prev, const void *e0, const int32_t *delay0,
+           int64_t n_patches, int64_t db, int64_t n_samples, int64_t ld, int64_t pad,
+           cudaStream_t st) {
+    const int64_t n_rows = n_patches * db;
+    SPB_CUDA(cudaMemsetAsync(e_total, 0, sizeof(T) * n_rows * ld, st));
+    if (e_prev) SPB_CUDA(cudaMemsetAsync(e_prev, 0, sizeof(T) * n_rows * ld, st));
+    if (n_rows == 0) return 0;
+    k_init_scatter<T><<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(
+        (T *)e_total, (T *)e_prev, (const T *)e0, delay0, n_rows, db, n_samples, ld, pad);
+    return check_launch("k_init_scatter");
+}
+
+template <typename T>
+int gather_t(const void *e_prev, void *g, const int64_t *seg_ptr, const int32_t *src,
+             const void *wgt, const int32_t *dly, int64_t n_patches, int64_t n_classes,
+             int64_t n_bands, int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
+             int64_t pad, cudaStream_t st) {
+    const int64_t n_j = j_hi - j_lo;
+    const int64_t n_work = n_classes * n_j * n_bands;
+    if (n_work == 0) return 0;
+    dim3 grid((unsigned)ceil_div(n_work, kWarpsPerCta), (unsigned)(t_pad / kTimeTile));
+    k_gather<T><<<grid, kWarpsPerCta * 32, 0, st>>>(
+        (const T *)e_prev, (T *)g, seg_ptr, src, (const T *)wgt, dly, n_patches,
+        n_classes, n_bands, j_lo, n_j, ld, pad);
+    return check_launch("k_gather");
+}
+
+template <typename T>
+int mix_t(const void *g, void *e_cur, void *e_total, const int64_t *seg_ptr,
+          const void *coef, int64_t n_patches, int64_t n_classes, int64_t n_dirs,
+          int64_t n_bands, int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
+          int64_t pad, cudaStream_t st) {
+    const int64_t n_j = j_hi - j_lo;
+    if (n_j == 0) return 0;
+    SPB_REQUIRE(n_j * n_bands <= 2147483647LL, "too many (patch, band) rows");
+    dim3 grid((unsigned)(n_j * n_bands), (unsigned)ceil_div(t_pad, 256));
+    k_mix<T><<<grid, 256, 0, st>>>(
+        (const T *)g, (T *)e_cur, (T *)e_total, seg_ptr, (const T *)coef, n_patches,
+        n_classes, n_dirs, n_bands, j_lo, t_pad, ld, pad);
+    return check_launch("k_mix");
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" {
+
+int spb_version(void) { return 100; }
+
+const char *spb_last_error(void) { return last_error().c_str(); }
+
+int spb_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    SPB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SPB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+int spb_exchange_layout(int64_t n_samples, int64_t max_delay, int dtype, int64_t *t_pad,
+                        int64_t *pad) {
+    SPB_REQUIRE(n_samples > 0 && max_delay >= 0, "n_samples > 0, max_delay >= 0");
+    SPB_REQUIRE(dtype == SPB_F64 || dtype == SPB_F32, "dtype");
+    *t_pad = round_up(n_samples, kTimeTile);
+    *pad = round_up(max_delay > 0 ? max_delay : 1, 32);
+    return 0;
+}
+
+int spb_exchange_init(void *e_total, void *e_prev, const void *e0, const int32_t *delay0,
+                      int64_t n_patches, int64_t db, int64_t n_samples, int64_t ld,
+                      int64_t pad, int dtype, void *stream) {
+    SPB_REQUIRE(e_total && e0 && delay0, "null pointer");
+    SPB_REQUIRE(ld >= pad + n_samples, "ld < pad + n_samples");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SPB_F64)
+        return init_t<double>(e_total, e_prev, e0, delay0, n_patches, db, n_samples, ld, pad, st);
+    if (dtype == SPB_F32)
+        return init_t<float>(e_total, e_prev, e0, delay0, n_patches, db, n_samples, ld, pad, st);
+    return fail(-1, "invalid argument", "dtype");
+}
+
+int spb_exchange_gather(const void *e_prev, void *g, const int64_t *seg_ptr,
+                        const int32_t *src, const void *wgt, const int32_t *dly,
+                        int64_t n_patches, int64_t n_classes, int64_t n_bands,
+                        int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
+                        int64_t pad, int dtype, void *stream) {
+    SPB_REQUIRE(e_prev && g && seg_ptr, "null pointer");
+    SPB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= n_patches, "receiver range");
+    SPB_REQUIRE(t_pad % kTimeTile == 0 && ld == pad + t_pad, "layout (use spb_exchange_layout)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SPB_F64)
+        return gather_t<double>(e_prev, g, seg_ptr, src, wgt, dly, n_patches, n_classes,
+                                n_bands, j_lo, j_hi, t_pad, ld, pad, st);
+    if (dtype == SPB_F32)
+        return gather_t<float>(e_prev, g, seg_ptr, src, wgt, dly, n_patches, n_classes,
+                               n_bands, j_lo, j_hi, t_pad, ld, pad, st);
+    return fail(-1, "invalid argument", "dtype");
+}
+
+int spb_exchange_mix(const void *g, void *e_cur, void *e_total, const int64_t *seg_ptr,
+                     const void *coef, int64_t n_patches, int64_t n_classes,
+                     int64_t n_dirs, int64_t n_bands, int64_t j_lo, int64_t j_hi,
+                     int64_t t_pad, int64_t ld, int64_t pad, int dtype, void *stream) {
+    SPB_REQUIRE(g && e_cur && e_total && seg_ptr && coef, "null pointer");
+    SPB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= n_patches, "receiver range");
+    SPB_REQUIRE(ld == pad + t_pad, "layout (use spb_exchange_layout)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SPB_F64)
+        return mix_t<double>(g, e_cur, e_total, seg_ptr, coef, n_patches, n_classes,
+                             n_dirs, n_bands, j_lo, j_hi, t_pad, ld, pad, st);
+    if (dtype == SPB_F32)
+        return mix_t<float>(g, e_cur, e_total, seg_ptr, coef, n_patches, n_classes,
+                            n_dirs, n_bands, j_lo, j_hi, t_pad, ld, pad, st);
+    return fail(-1, "invalid argument", "dtype");
+}
+
+int spb_energy_exchange(const void *e0, const int32_t *delay0, const int64_t *seg_ptr,
+                        const int32_t *src, const void *wgt, const int32_t *dly,
+                        const void *coef, int64_t n_patches, int64_t n_classes,
+                        int64_t n_dirs, int64_t n_bands, int64_t n_samples,
+                        int64_t t_pad, int64_t pad, int64_t max_order, void *e_total,
+                        void *e_a, void *e_b, void *g, int dtype, void *stream) {
+    const int64_t ld = pad + t_pad;
+    const int64_t db = n_dirs * n_bands;
+    int rc = spb_exchange_init(e_total, max_order >= 1 ? e_a : nullptr, e0, delay0,
+                               n_patches, db, n_samples, ld, pad, dtype, stream);
+    if (rc) return rc;
+    if (max_order < 1) return 0;
+    SPB_REQUIRE(e_a && e_b && g, "null workspace");
+    // e_b's pre-roll must be zero as well (e_a was zeroed by init)
+    const size_t esz = dtype == SPB_F64 ? 8 : 4;
+    SPB_CUDA(cudaMemsetAsync(e_b, 0, esz * n_patches * db * ld, (cudaStream_t)stream));
+    void *prev = e_a, *cur = e_b;
+    for (int64_t k = 0; k < max_order; ++k) {
+        rc = spb_exchange_gather(prev, g, seg_ptr, src, wgt, dly, n_patches, n_classes,
+                                 n_bands, 0, n_patches, t_pad, ld, pad, dtype, stream);
+        if (rc) return rc;
+        rc = spb_exchange_mix(g, cur, e_total, seg_ptr, coef, n_patches, n_classes,
+                              n_dirs, n_bands, 0, n_patches, t_pad, ld, pad, dtype, stream);
+        if (rc) return rc;
+        void *tmp = prev; prev = cur; cur = tmp;
+    }
+    return 0;
+}
+
+int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *shift,
+                     const void *scale, int64_t n_receivers, int64_t n_patches,
+                     int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
+                     int64_t pad, void *mono, void *partial, int64_t n_split, int dtype,
+                     void *stream) {
+    SPB_REQUIRE(e_total && rdir && shift && scale && mono && partial, "null pointer");
+    SPB_REQUIRE(n_split >= 1 && n_split <= 65535, "n_split");
+    SPB_REQUIRE(n_receivers * n_bands <= 65535, "n_receivers * n_bands > 65535: batch the receivers");
+    if (n_receivers == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)ceil_div(n_samples, 256), (unsigned)(n_receivers * n_bands),
+              (unsigned)n_split);
+    const int64_t n_out = n_receivers * n_bands * n_samples;
+    if (dtype == SPB_F64) {
+        k_collect_partial<double><<<grid, 256, 0, st>>>(
+            (const double *)e_total, rdir, shift, (const double *)scale, n_patches, n_dirs,
+            n_bands, n_samples, ld, pad, (double *)partial, n_split);
+        int rc = check_launch("k_collect_partial");
+        if (rc) return rc;
+        k_collect_reduce<double><<<(unsigned)ceil_div(n_out, 256), 256, 0, st>>>(
+            (const double *)partial, (double *)mono, n_out, n_split);
+        return check_launch("k_collect_reduce");
+    }
+    if (dtype == SPB_F32) {
+        k_collect_partial<float><<<grid, 256, 0, st>>>(
+            (const float *)e_total, rdir, shift, (const float *)scale, n_patches, n_dirs,
+            n_bands, n_samples, ld, pad, (float *)partial, n_split);
+        int rc = check_launch("k_collect_partial");
+        if (rc) return rc;
+        k_collect_reduce<float><<<(unsigned)ceil_div(n_out, 256), 256, 0, st>>>(
+            (const float *)partial, (float *)mono, n_out, n_split);
+        return check_launch("k_collect_reduce");
+    }
+    return fail(-1, "invalid argument", "dtype");
+}
+
+int spb_collect_patchwise(const void *e_total, const int32_t *rdir, const int32_t *shift,
+                          const void *scale, int64_t n_receivers, int64_t n_patches,
+                          int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
+                          int64_t pad, void *out, int dtype, void *stream) {
+    SPB_REQUIRE(e_total && rdir && shift && scale && out, "null pointer");
+    const int64_t rows = n_receivers * n_patches * n_bands;
+    if (rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SPB_REQUIRE(rows <= 2147483647LL, "too many (receiver, patch, band) rows");
+    dim3 grid((unsigned)rows, (unsigned)ceil_div(n_samples, 256));
+    if (dtype == SPB_F64)
+        k_collect_patchwise<double><<<grid, 256, 0, st>>>(
+            (const double *)e_total, rdir, shift, (const double *)scale, n_patches, n_dirs,
+            n_bands, n_samples, ld, pad, (double *)out);
+    else if (dtype == SPB_F32)
+        k_collect_patchwise<float><<<grid, 256, 0, st>>>(
+            (const float *)e_total, rdir, shift, (const float *)scale, n_patches, n_dirs,
+            n_bands, n_samples, ld, pad, (float *)out);
+    else
+        return fail(-1, "invalid argument", "dtype");
+    return check_launch("k_collect_patchwise");
+}
+
+}  // extern "C"

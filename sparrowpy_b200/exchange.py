@@ -1,0 +1,175 @@
+"""Host side of the energy exchange and receiver collection.
+
+Mirrors the array-level operators of the reference
+(``_energy_exchange_init_energy``, ``_energy_exchange``, ``_collect_receiver_energy``;
+reference RadiosityFast.py:1037-1185) on top of the C ABI in
+include/sparrow_b200.h.  PyTorch is used for device memory, streams and index
+bookkeeping only; all arithmetic on the energy histograms runs in the CUDA
+kernels of csrc/exchange.cu.
+"""
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class PairTables:
+    """Factored ``form_factors_tilde`` in receiver-major CSR form (device)."""
+    seg_ptr: torch.Tensor      # (C*N + 1,) int64
+    src: torch.Tensor          # (nnz,) int32   sender patch * D + outgoing dir
+    wgt: torch.Tensor          # (nnz,) dtype   directed form factor
+    dly: torch.Tensor          # (nnz,) int32   delay bins
+    coef: torch.Tensor         # (C, D, B) dtype  exp(-air) * brdf
+    n_patches: int
+    n_classes: int
+    n_dirs: int
+    n_bands: int
+    max_delay: int
+    n_directed: int            # directed pairs before dropping delay >= T
+    dtype: int
+
+
+def directed_pairs(pairs, ff_pairs, areas):
+    """Expand visible pairs (lo < hi) into directed pairs.
+
+    Entry 2p is lo->hi, entry 2p+1 is hi->lo -- the order in which the reference
+    loop visits them (RadiosityFast.py:1124-1131).  The reverse form factor is
+    ``ff * A_receiver / A_sender`` (RadiosityFast.py:1255-1256).
+    """
+    lo, hi = pairs[:, 0].long(), pairs[:, 1].long()
+    sender = torch.stack([lo, hi], dim=1).reshape(-1)
+    receiver = torch.stack([hi, lo], dim=1).reshape(-1)
+    ff_rev = ff_pairs * areas[lo] / areas[hi]
+    ff = torch.stack([ff_pairs, ff_rev], dim=1).reshape(-1)
+    return sender, receiver, ff
+
+
+def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches,
+                      n_samples, dtype):
+    """Sort directed pairs into segments (class, receiver) and drop pairs whose
+    delay is >= n_samples (they contribute nothing, RadiosityFast.py:1137-1140)."""
+    code = _lib.dtype_code(dtype)
+    tdt = _lib.torch_dtype(code)
+    n_classes, n_dirs, n_bands = coef.shape
+    n_directed = int(sender.numel())
+    keep = delay < n_samples
+    sender, receiver, ff = sender[keep], receiver[keep], ff[keep]
+    delay, out_dir, cls = delay[keep], out_dir[keep], cls[keep]
+    seg = cls.long() * n_patches + receiver.long()
+    key = seg * n_patches + sender.long()
+    order = torch.argsort(key)
+    seg = seg[order]
+    counts = torch.bincount(seg, minlength=n_classes * n_patches)
+    seg_ptr = torch.zeros(n_classes * n_patches + 1, dtype=torch.int64,
+                          device=sender.device)
+    seg_ptr[1:] = torch.cumsum(counts, 0)
+    src = (sender[order] * n_dirs + out_dir[order].long()).to(torch.int32)
+    max_delay = int(delay.max().item()) if delay.numel() else 0
+    return PairTables(
+        seg_ptr=seg_ptr.contiguous(), src=src.contiguous(),
+        wgt=ff[order].to(tdt).contiguous(),
+        dly=delay[order].to(torch.int32).contiguous(),
+        coef=coef.to(tdt).contiguous(), n_patches=int(n_patches),
+        n_classes=int(n_classes), n_dirs=int(n_dirs), n_bands=int(n_bands),
+        max_delay=max_delay, n_directed=n_directed, dtype=code)
+
+
+class EnergyHistogram:
+    """(patch, direction, band, time) histogram in the padded-row device layout."""
+
+    def __init__(self, data, n_patches, n_dirs, n_bands, n_samples, pad):
+        self.data = data                    # (N*D*B, LD)
+        self.n_patches, self.n_dirs = n_patches, n_dirs
+        self.n_bands, self.n_samples, self.pad = n_bands, n_samples, pad
+
+    @property
+    def ld(self):
+        return self.data.shape[1]
+
+    def dense(self):
+        """(N, D, B, T) view without padding (still on the device)."""
+        v = self.data[:, self.pad:self.pad + self.n_samples]
+        return v.reshape(self.n_patches, self.n_dirs, self.n_bands, self.n_samples)
+
+
+class ExchangeWorkspace:
+    """Device buffers of one exchange run: E_total, ping-pong E_a/E_b and G."""
+
+    def __init__(self, tables, n_samples, device, need_orders=True):
+        t = tables
+        self.t_pad, self.pad = _lib.exchange_layout(n_samples, t.max_delay, t.dtype)
+        self.ld = self.t_pad + self.pad
+        self.n_samples = n_samples
+        tdt = _lib.torch_dtype(t.dtype)
+        rows = t.n_patches * t.n_dirs * t.n_bands
+        self.e_total = torch.empty((rows, self.ld), dtype=tdt, device=device)
+        if need_orders:
+            self.e_a = torch.empty((rows, self.ld), dtype=tdt, device=device)
+            self.e_b = torch.empty((rows, self.ld), dtype=tdt, device=device)
+            # rows of empty segments are never written nor read
+            self.g = torch.empty((t.n_classes * t.n_patches * t.n_bands, self.ld),
+                                 dtype=tdt, device=device)
+        else:
+            self.e_a = self.e_b = self.g = None
+
+
+def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
+    """``_energy_exchange`` (RadiosityFast.py:1073-1145) on the current device.
+
+    e0: (N, D, B) device tensor; delay0: (N,) int32 source->patch delay bins.
+    Returns an :class:`EnergyHistogram` holding sum_{k<=K} E_k.
+    """
+    t = tables
+    tdt = _lib.torch_dtype(t.dtype)
+    device = e0.device
+    ws = workspace or ExchangeWorkspace(t, n_samples, device, need_orders=max_order >= 1)
+    e0 = e0.to(tdt).contiguous()
+    delay0 = delay0.to(torch.int32).contiguous()
+    _lib.call("spb_energy_exchange", e0, delay0, t.seg_ptr, t.src, t.wgt, t.dly, t.coef,
+              t.n_patches, t.n_classes, t.n_dirs, t.n_bands, n_samples, ws.t_pad, ws.pad,
+              int(max_order), ws.e_total, ws.e_a, ws.e_b, ws.g, _lib.I32(t.dtype),
+              _lib.stream_ptr())
+    return EnergyHistogram(ws.e_total, t.n_patches, t.n_dirs, t.n_bands, n_samples, ws.pad)
+
+
+def collect_mono(hist, rdir, shift, scale, n_split=None):
+    """Sum of all patch histograms at each receiver, (R, B, T)
+    (``collect_energy_receiver_mono``, RadiosityFast.py:570-602 / :1148-1185).
+
+    rdir, shift: (R, N) int32; scale: (R, N, B).
+    """
+    n_rcv = rdir.shape[0]
+    tdt = hist.data.dtype
+    code = _lib.dtype_code(tdt)
+    if n_split is None:
+        n_split = max(1, min(64, hist.n_patches // 256))
+    out = torch.empty((n_rcv, hist.n_bands, hist.n_samples), dtype=tdt,
+                      device=hist.data.device)
+    # grid.y carries receiver*band: batch the receivers if there are many
+    step = max(1, 65535 // hist.n_bands)
+    for r0 in range(0, n_rcv, step):
+        r1 = min(n_rcv, r0 + step)
+        partial = torch.empty((n_split, r1 - r0, hist.n_bands, hist.n_samples), dtype=tdt,
+                              device=hist.data.device)
+        _lib.call("spb_collect_mono", hist.data, rdir[r0:r1].contiguous(),
+                  shift[r0:r1].contiguous(), scale[r0:r1].to(tdt).contiguous(), r1 - r0,
+                  hist.n_patches, hist.n_dirs, hist.n_bands, hist.n_samples, hist.ld,
+                  hist.pad, out[r0:r1], partial, n_split, _lib.I32(code),
+                  _lib.stream_ptr())
+    return out
+
+
+def collect_patchwise(hist, rdir, shift, scale):
+    """Per-patch histograms at each receiver, (R, N, B, T)
+    (``collect_energy_receiver_patchwise``, RadiosityFast.py:660-752)."""
+    n_rcv = rdir.shape[0]
+    tdt = hist.data.dtype
+    code = _lib.dtype_code(tdt)
+    out = torch.empty((n_rcv, hist.n_patches, hist.n_bands, hist.n_samples), dtype=tdt,
+                      device=hist.data.device)
+    _lib.call("spb_collect_patchwise", hist.data, rdir.contiguous(), shift.contiguous(),
+              scale.to(tdt).contiguous(), n_rcv, hist.n_patches, hist.n_dirs, hist.n_bands,
+              hist.n_samples, hist.ld, hist.pad, out, _lib.I32(code), _lib.stream_ptr())
+    return out

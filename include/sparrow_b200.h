@@ -126,6 +126,78 @@ int spb_collect_patchwise(const void *e_total, const int32_t *rdir,
                           int64_t n_bands, int64_t n_samples, int64_t ld, int64_t pad,
                           void *out, int dtype, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Geometry baking.  All coordinates are FP64 (the reference's dtype); boolean and
+ * integer outputs are bit-identical to the reference, floating-point outputs agree
+ * to <= 1e-6 relative (measured ~1e-12).
+ * ------------------------------------------------------------------------- */
+
+/* Per-surface data that `_point_in_polygon` (geometry.py:614-686) derives from a
+ * blocking polygon: rotation to the plane, rotated vertices, side normals.
+ * surf_points: [M, 4, 3], surf_normals: [M, 3]; blockers: spb_blocker_bytes(M). */
+size_t spb_blocker_bytes(int64_t m);
+int spb_make_blockers(const double *surf_points, const double *surf_normals, int64_t m,
+                      int nvert, void *blockers, void *stream);
+
+/* `_check_patch2patch_visibility` (geometry.py:750-797): vis[i,j] (uint8, [N,N]) =
+ * AND over all M surfaces of `_basic_visibility(c_i, c_j, surface)` for i < j, 0
+ * elsewhere. */
+int spb_visibility_p2p(const double *centers, int64_t n, const void *blockers, int64_t m,
+                       uint8_t *vis, void *stream);
+
+/* `_check_point2patch_visibility` (geometry.py:799-839) for a batch of points:
+ * vis[r,j] ([R,N] uint8). */
+int spb_visibility_pt2p(const double *points, int64_t n_points, const double *centers,
+                        int64_t n, const void *blockers, int64_t m, uint8_t *vis,
+                        void *stream);
+
+/* `patch2patch_ff_universal` (universal.py:12-96): ff[p] for visible pair p =
+ * (i, j), i < j.  The Stokes call handles every pair that shares no vertex and
+ * flags the others (nusselt_flag[p] = 1); the Nusselt call integrates the flagged
+ * pairs listed in todo (integration.py:116-289). */
+int spb_form_factors_stokes(const double *pts, const double *areas, const int32_t *pairs,
+                            int64_t n_pairs, double *ff, uint8_t *nusselt_flag, void *stream);
+int spb_form_factors_nusselt(const double *pts, const double *normals, const int32_t *pairs,
+                             const int64_t *todo, int64_t n_todo, double *ff, void *stream);
+
+/* `_source2patch_energy_universal` (universal.py:98-147) + `_add_directional`
+ * (RadiosityFast.py:988-1034): distance[j] (0 for invisible patches), e0[j,d,b];
+ * energy[j,b] (before the BRDF, optional).  src: 3 doubles on the device. */
+int spb_source_energy(const double *src, const double *centers, const double *pts,
+                      const uint8_t *vis, const double *air, const int64_t *patch_to_wall,
+                      const double *vi, int64_t n_in, const double *brdf,
+                      const int64_t *brdf_index, int64_t n_out, int64_t n_bands, int64_t n,
+                      double *distance, double *e0, double *energy, void *stream);
+
+/* Receiver side of `_collect_energy_patches` (RadiosityFast.py:711-748) for a batch
+ * of receivers: factor[r,k] (universal.py:149-160), rdir[r,k] (:728-730), delay[r,k]
+ * = ceil(dist/c/dt) (:1178-1179), shift = delay mod T, scale[r,k,b] = factor *
+ * exp(-air[b] * dist). */
+int spb_receiver_factors(const double *rcv, int64_t n_rcv, const double *centers,
+                         const double *pts, const uint8_t *vis, const double *air,
+                         const int64_t *patch_to_wall, const double *vo, int64_t n_out,
+                         int64_t n_bands, int64_t n, double speed_of_sound, double dt,
+                         int64_t n_samples, double *factor, int32_t *rdir, int32_t *delay,
+                         int32_t *shift, double *scale, void *stream);
+
+/* Per-pair tables behind form_factors_tilde: dist[p] (numpy 1-D norm model,
+ * RadiosityFast.py:538-543), out_dir[2p+e] (:403-414), in_dir[2p+e] (:1386-1390);
+ * directed entry 2p = lo->hi, 2p+1 = hi->lo. */
+int spb_pair_geometry(const double *centers, const int64_t *patch_to_wall,
+                      const int32_t *pairs, int64_t n_pairs, const double *vi, int64_t n_in,
+                      const double *vo, int64_t n_out, double *dist, int32_t *out_dir,
+                      int32_t *in_dir, void *stream);
+
+/* int(dist / c / dt) (RadiosityFast.py:1067-1068, :1135-1136) */
+int spb_delay_bins(const double *dist, int64_t count, double speed_of_sound, double dt,
+                   int32_t *out, void *stream);
+
+/* test probes of the device arithmetic model (x87 norm, `_basic_visibility`) */
+int spb_probe_norms(const double *v, int64_t count, int dim, double *out, void *stream);
+int spb_probe_basic_visibility(const double *a, const double *b, const void *blockers,
+                               int64_t count, uint8_t *visible, uint8_t *in_a, uint8_t *in_b,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

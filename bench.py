@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 energy-exchange hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--dtype f64]
+    python bench.py --impl reference ...      # CPU arm: oracle port on the host cores
+
+A "step" is one full ETC: `_energy_exchange` with the configuration's reflection
+order count on the baked scene (pair tables resident).  Metric: patch-pair x
+time-bin exchanges per second, X = 2 * P * T * K_orders per ETC.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+# ---------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------
+CONFIGS = {
+    # name: scene, patch, (n_az, colatitudes) or None, bands, T, orders, source, receivers
+    "c1": dict(scene=("shoebox", (5, 6, 4)), patch=1.0, dirs=None, bands=1, n_samples=1000,
+               orders=150, source=(2.0, 2.0, 2.0), receivers=[(2.0, 3.0, 2.0)],
+               scattering=1.0, absorption=0.1,
+               desc="C1 shoebox 5x6x4 m, 1 m patches, diffuse, 1 band, T=1000, K=150"),
+    "c2": dict(scene=("shoebox", (5, 6, 4)), patch=0.2, dirs=(8, (30.0, 60.0)), bands=6,
+               n_samples=1000, orders=20, source=(2.0, 2.0, 2.0), receivers=[(2.0, 3.0, 2.0)],
+               scattering=0.5, absorption=0.1,
+               desc="C2 shoebox 5x6x4 m, 0.2 m patches (N=3700), 16 directions, 6 bands, "
+                    "T=1000, K=20"),
+    "c4": dict(scene=("canyon", 1.0), patch=1.0, dirs=None, bands=1, n_samples=2000,
+               orders=50, source=(60.0, 30.0, 1.5),
+               receivers=[(10.0, 30.0, 1.5), (50.0, 28.0, 1.5), (90.0, 32.0, 1.5),
+                          (110.0, 30.0, 1.5)],
+               scattering=1.0, absorption=0.2,
+               desc="C4 street canyon 120x60 m + 5 buildings, 1 m patches (N=19200), "
+                    "diffuse, T=2000, K=50"),
+    # reduced variants for quick checks
+    "c2s": dict(scene=("shoebox", (5, 6, 4)), patch=0.5, dirs=(8, (30.0, 60.0)), bands=6,
+                n_samples=1000, orders=20, source=(2.0, 2.0, 2.0),
+                receivers=[(2.0, 3.0, 2.0)], scattering=0.5, absorption=0.1,
+                desc="C2-small shoebox 5x6x4 m, 0.5 m patches (N=592), 16 dirs, 6 bands"),
+}
+SPEED_OF_SOUND = 343.2
+DT = 1e-3
+
+
+def build_scene(cfg, dtype):
+    """Bake the scene on the current GPU through the public class API."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf, scenes
+    kind, arg = cfg["scene"]
+    walls = scenes.shoebox(*arg) if kind == "shoebox" else scenes.street_canyon(0, arg)
+    rad = sp.DirectionalRadiosityFast.from_polygon([sp.Polygon(*w) for w in walls],
+                                                   cfg["patch"], dtype=dtype)
+    nb = cfg["bands"]
+    freqs = 125.0 * 2.0 ** np.arange(nb) if nb > 1 else np.array([1000.0])
+    if cfg["dirs"] is not None:
+        dirs, weights = scenes.hemisphere_directions(*cfg["dirs"])
+    else:
+        dirs, weights = np.array([[0.0, 0.0, 1.0]]), np.array([1.0])
+    brdf = scenes.brdf_from_scattering(dirs, weights, np.full(nb, cfg["scattering"]),
+                                       np.full(nb, cfg["absorption"]))
+    coords = pf.Coordinates.from_cartesian(dirs, weights=weights)
+    rad.set_wall_brdf(np.arange(rad.n_walls), pf.FrequencyData(brdf, freqs), coords, coords)
+    air = 1e-4 * 2.0 ** np.arange(nb) if nb > 1 else np.zeros(1)
+    rad.set_air_attenuation(pf.FrequencyData(air, freqs))
+    rad.bake_geometry()
+    rad.init_source_energy(pf.Coordinates(*cfg["source"]))
+    return rad
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                    timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names)
+                   if any(len(s) > 2 + k and s[2 + k].lower().startswith("active")
+                          for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the oracle port of `_energy_exchange` on a bounded pair sample
+# ---------------------------------------------------------------------------
+def cpu_exchange_rate(rad, cfg, n_threads, budget_s=12.0, log=None):
+    """Time the oracle's `_energy_exchange` (one order) on a random subset of the
+    visible pairs and extrapolate to the full pair list (work is exactly linear in
+    the number of pairs and orders, RadiosityFast.py:1121-1144).
+
+    Returns dict(value=exchanges/s for the full configuration, ...)."""
+    from oracle import oracle as orc
+    b = rad._baked
+    n, t_len = rad.n_patches, cfg["n_samples"]
+    pairs = b["pairs"].cpu().numpy()
+    p_full = pairs.shape[0]
+    e0 = rad._energy_init_source
+    d0 = rad._distance_patches_to_source
+    coef = b["coef"].cpu().numpy()
+    ff_dir = b["ff_dir"].cpu().numpy()
+    cls = b["cls"].cpu().numpy()
+    out_dir = b["out_dir"].cpu().numpy().astype(np.int64)
+    delay = np.repeat((b["dist"].cpu().numpy() / SPEED_OF_SOUND / DT).astype(np.int64), 2)
+    rng = np.random.default_rng(0)
+
+    def run(n_sample, orders=1):
+        sel = np.sort(rng.choice(p_full, size=n_sample, replace=False)) if n_sample else \
+            np.zeros(0, np.int64)
+        dsel = np.stack([2 * sel, 2 * sel + 1], 1).reshape(-1)
+        tilde = ff_dir[dsel, None, None] * coef[cls[dsel]]
+        t0 = time.perf_counter()
+        orc.energy_exchange(e0, d0, pairs[sel], tilde, out_dir[dsel], delay[dsel], t_len,
+                            SPEED_OF_SOUND, DT, orders, n_threads=n_threads)
+        return time.perf_counter() - t0
+
+    t_fixed = run(0)                       # zeroing + accumulation passes, no pairs
+    # Bound the sample a priori: one visible pair costs 2*D*B*T multiply-adds per
+    # order and a host core sustains < 4e9 of them per second on this loop, so the
+    # probe's timing noise can never blow the budget.
+    n_dir, n_band = coef.shape[1], coef.shape[2]
+    floor_per_pair = 2.0 * n_dir * n_band * t_len / (4e9 * max(1, n_threads))
+    cap = int(max(200, budget_s / floor_per_pair))
+    probe = int(min(p_full, max(200, cap // 20)))
+    t_probe = run(probe)
+    per_pair = max(t_probe - t_fixed, floor_per_pair * probe) / probe
+    n_sample = int(min(p_full, cap, max(probe, (budget_s - t_fixed) / per_pair)))
+    t_sample = run(n_sample)
+    per_pair = max(t_sample - t_fixed, 1e-9) / n_sample
+    t_order_full = t_fixed + per_pair * p_full      # one order on the full pair list
+    value = 2.0 * p_full * t_len / t_order_full
+    if log:
+        log(f"cpu baseline: fixed {t_fixed:.2f}s, {n_sample} pairs in {t_sample:.2f}s, "
+            f"full order ~{t_order_full:.1f}s")
+    return dict(value=value, seconds_per_order=t_order_full, n_sample=n_sample,
+                t_sample=t_sample, t_fixed=t_fixed,
+                sample=(f"1 reflection order on {n_sample} of {p_full} visible pairs "
+                        f"(random, seed 0), full N/D/B/T; extrapolated linearly in pairs "
+                        f"and orders; fixed per-order passes {t_fixed:.2f}s included"))
+
+
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("SPB_BENCH_CONFIG", "c2"),
+                    choices=sorted(CONFIGS))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def log(msg):
+        if args.verbose and rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    import torch
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world, log)
+        return
+
+    import torch.distributed as dist
+    from sparrowpy_b200 import _lib, bake, distributed, exchange
+
+    _lib.load()
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    t0 = time.time()
+    rad = build_scene(cfg, args.dtype)
+    torch.cuda.synchronize()
+    log(f"baked {args.config}: N={rad.n_patches} P={rad._baked['pairs'].shape[0]} "
+        f"in {time.time() - t0:.1f}s")
+    n_samples, orders = cfg["n_samples"], cfg["orders"]
+    tables = rad._pair_tables(SPEED_OF_SOUND, DT, n_samples)
+    n_pairs = int(rad._baked["pairs"].shape[0])
+    n_dir, n_band = tables.n_dirs, tables.n_bands
+    x_per_step = 2.0 * n_pairs * n_samples * orders
+    code = _lib.dtype_code(args.dtype)
+    esize = 8 if code == _lib.F64 else 4
+
+    sx = distributed.ShardedExchange(tables, n_samples, dev)
+    e0_dev = rad._e0_dev.to(_lib.torch_dtype(code)).contiguous()
+    delay0 = bake.delay_bins(rad._d0_dev, SPEED_OF_SOUND, DT)
+    st = torch.cuda.current_stream()
+    gather_events = []
+
+    def timed_order(prev, cur, total):
+        t = sx.t
+        c32, sp = _lib.I32(t.dtype), _lib.stream_ptr()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(st)
+        _lib.call("spb_exchange_gather", prev, sx.g, t.seg_ptr, t.src, t.wgt, t.dly,
+                  t.n_patches, t.n_classes, t.n_bands, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld,
+                  sx.pad, c32, sp)
+        ev1.record(st)
+        gather_events.append((ev0, ev1))
+        _lib.call("spb_exchange_mix", sx.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
+                  t.n_classes, t.n_dirs, t.n_bands, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld,
+                  sx.pad, c32, sp)
+
+    sx.compute = timed_order
+
+    def step():
+        sx.init(e0_dev, delay0)
+        return sx.run(orders)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    gather_events.clear()
+    launches_per_step = orders * 2 + 4          # gather+mix per order, init (memsets+scatter)
+    with ClockSampler(local_rank) as clocks:
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev_a.record(st)
+        for _ in range(args.steps):
+            step()
+        ev_b.record(st)
+        barrier()
+        elapsed_ms = ev_a.elapsed_time(ev_b)
+    gather_ms = [a.elapsed_time(b) for a, b in gather_events]
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = x_per_step / (ms_per_step * 1e-3)
+
+    # -- roofline of the dominant kernel (k_gather), this rank's share ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    share = (sx.j_hi - sx.j_lo) / max(rad.n_patches, 1)
+    # algorithmic bytes per pair.bin exchange = B*(1+2D)*sizeof; one gather
+    # launch processes this rank's directed pairs x T bins of one order
+    alg_bytes_launch = 2.0 * n_pairs * share * n_samples * n_band * (1 + 2 * n_dir) * esize
+    gather_avg_ms = float(np.mean(gather_ms)) if gather_ms else float("nan")
+    achieved = alg_bytes_launch / (gather_avg_ms * 1e-3) / 1e9
+    # executed FMAs of the factored kernel: directed pairs x B x T_pad per order
+    fma_launch = float(tables.src.numel()) * share * n_band * sx.t_pad
+    fma_tflops = 2.0 * fma_launch / (gather_avg_ms * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "kernel": "k_gather",
+                "peak_source": peak_src, "avg_launch_ms": gather_avg_ms,
+                "launches_timed": len(gather_ms),
+                "share_of_step": sum(gather_ms) / max(elapsed_ms, 1e-9),
+                "executed_fma_tflops": fma_tflops,
+                "fma_pipe_nominal_tflops": 37.0 if code == _lib.F64 else 75.0,
+                "note": "algorithmic bytes are those of the reference's dense-tilde "
+                        "formulation; the factored kernel moves far fewer, so frac can "
+                        "exceed 1 (see DESIGN.md)"}
+
+    # -- end to end through the public operator with HOST buffers ---------------------
+    e2e = None
+    if world == 1:
+        e0_host = rad._e0_dev.cpu().pin_memory()
+        d0_host = rad._d0_dev.cpu().pin_memory()
+        n, d, b = e0_host.shape
+        out_host = torch.empty((n, d, b, n_samples), dtype=_lib.torch_dtype(code)).pin_memory()
+        ws = exchange.ExchangeWorkspace(tables, n_samples, dev)
+
+        def e2e_step():
+            exchange.energy_exchange_host(tables, e0_host, d0_host, SPEED_OF_SOUND, DT,
+                                          n_samples, orders, out_host, workspace=ws)
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        n_e2e = max(2, min(args.steps, 5))
+        t1 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t1) / n_e2e
+        e2e = {"value": x_per_step / e2e_s, "unit": "pair*bin exchanges/s",
+               "h2d_bytes_per_step": int(e0_host.numel() * 8 + d0_host.numel() * 8),
+               "d2h_bytes_per_step": int(out_host.numel() * esize),
+               "ms_per_step": e2e_s * 1e3,
+               "api": "sparrowpy_b200.exchange.energy_exchange_host (host E0/d0 in pinned "
+                      "memory -> device, K orders, full ETC -> pinned host)"}
+
+    # -- CPU baseline on the host cores (rank 0, N = 1 only) ----------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = cpu_exchange_rate(rad, cfg, n_threads=1, log=log)
+        cpu = {"value": res["value"], "unit": "pair*bin exchanges/s", "cores": 1,
+               "kind": "port", "sample": res["sample"],
+               "seconds_per_etc": res["seconds_per_order"] * orders}
+
+    if rank == 0:
+        line = {
+            "metric": "patch-pair*time-bin exchanges/s (energy exchange, s per ETC alongside)",
+            "value": value, "unit": "pair*bin exchanges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "seconds_per_etc": ms_per_step * 1e-3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic", "gpu_launches": int(launches_per_step * args.steps),
+            "config": {"workload": cfg["desc"], "name": args.config,
+                       "n_patches": rad.n_patches, "visible_pairs": n_pairs,
+                       "directed_pairs_kept": int(tables.src.numel()),
+                       "n_directions": n_dir, "n_bands": n_band, "n_samples": n_samples,
+                       "reflection_orders": orders,
+                       "exchanges_per_etc": x_per_step,
+                       "l2": "inputs larger than L2" if
+                       rad.n_patches * n_dir * n_band * sx.ld * esize > 126e6 * 2
+                       else "working set fits L2 (small config, no flush)",
+                       "parallelism": f"receiver shards x{world}" if world > 1 else "1 GPU"},
+            "clocks": clocks.summary(), "roofline": roofline,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args, cfg, rank, world, log):
+    """CPU arm: the oracle port of the reference's `_energy_exchange` on the host
+    cores (all threads), bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import oracle as orc
+    orc.build()
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference",
+                          "unavailable": "scene baking needs the CUDA path; no GPU here"}))
+        return
+    rad = build_scene(cfg, "f64")
+    torch.cuda.synchronize()
+    threads = orc.max_threads()
+    n_pairs = int(rad._baked["pairs"].shape[0])
+    orders = cfg["orders"]
+    x_per_step = 2.0 * n_pairs * cfg["n_samples"] * orders
+    budget = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    res = None
+    for k in range(args.warmup + args.steps):
+        res = cpu_exchange_rate(rad, cfg, n_threads=threads, budget_s=budget, log=log)
+        if k >= args.warmup:
+            vals.append(res["value"])
+    value = float(np.mean(vals)) if vals else float("nan")
+    line = {
+        "impl": "reference",
+        "metric": "patch-pair*time-bin exchanges/s (energy exchange, s per ETC alongside)",
+        "value": value, "unit": "pair*bin exchanges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": x_per_step / value * 1e3 if value == value else None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": cfg["desc"], "name": args.config, "n_patches": rad.n_patches,
+                   "visible_pairs": n_pairs, "reflection_orders": orders},
+        "cpu_baseline": {"value": value, "unit": "pair*bin exchanges/s", "cores": threads,
+                         "kind": "port", "sample": res["sample"] if res else ""},
+        "e2e": {"value": value, "unit": "pair*bin exchanges/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": "oracle port of _energy_exchange (time-sliced over all host threads, "
+                "bit-identical to the serial reference order); the reference itself is "
+                "single-threaded here (RadiosityFast.py:1396)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

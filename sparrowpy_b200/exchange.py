@@ -173,3 +173,25 @@ def collect_patchwise(hist, rdir, shift, scale):
               scale.to(tdt).contiguous(), n_rcv, hist.n_patches, hist.n_dirs, hist.n_bands,
               hist.n_samples, hist.ld, hist.pad, out, _lib.I32(code), _lib.stream_ptr())
     return out
+
+
+def energy_exchange_host(tables, e0_host, distance0_host, speed_of_sound, dt, n_samples,
+                         max_order, out_host=None, workspace=None):
+    """``_energy_exchange`` (RadiosityFast.py:1073-1145) with HOST buffers in and out:
+    the call a maintainer binds in place of the numba kernel.
+
+    e0_host: (N, D, B) float64, distance0_host: (N,) float64 source->patch distances
+    (torch CPU tensors, ideally pinned, or numpy arrays).  The full (N, D, B, T)
+    histogram is written to ``out_host`` (allocated pinned when None) and returned.
+    """
+    from . import bake
+    dev = tables.seg_ptr.device
+    e0 = torch.as_tensor(e0_host).to(dev, non_blocking=True)
+    d0 = torch.as_tensor(distance0_host).to(dev, non_blocking=True)
+    delay0 = bake.delay_bins(d0, speed_of_sound, dt)
+    hist = energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=workspace)
+    dense = hist.dense()
+    if out_host is None:
+        out_host = torch.empty(dense.shape, dtype=dense.dtype).pin_memory()
+    out_host.copy_(dense)
+    return out_host

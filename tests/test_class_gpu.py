@@ -1,0 +1,129 @@
+"""The drop-in class end to end on the GPU, driven exactly like the reference class
+was when the golden fixtures were made (tests/golden/make_golden.py::run_scene)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+SCENES = ["scene_cube05", "scene_c1", "scene_occluder", "scene_directional",
+          "scene_canyon01"]
+TOL = {"f64": 1e-6, "f32": 1e-4}
+
+
+def run_class(g, dtype="f64"):
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    walls = [sp.Polygon(p, u, n) for p, u, n in
+             zip(g["walls_points"], g["walls_up"], g["walls_normal"])]
+    rad = sp.DirectionalRadiosityFast.from_polygon(walls, float(g["patch_size"]),
+                                                   dtype=dtype)
+    if "brdf_dirs" in g:
+        coords = pf.Coordinates.from_cartesian(g["brdf_dirs"], weights=g["brdf_weights"])
+        brdf, bidx = g["brdf"], g["brdf_index"]
+        for m in range(brdf.shape[0]):
+            rad.set_wall_brdf(np.nonzero(bidx == m)[0],
+                              pf.FrequencyData(brdf[m] / np.pi, g["frequencies"]),
+                              coords, coords)
+        rad.set_air_attenuation(pf.FrequencyData(g["air_attenuation"], g["frequencies"]))
+    rad.bake_geometry()
+    rad.init_source_energy(pf.Coordinates(*g["source"]))
+    rad.calculate_energy_exchange(float(g["speed_of_sound"]), float(g["dt"]),
+                                  float(g["duration"]),
+                                  max_reflection_order=int(g["max_order"]))
+    return rad
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_pipeline_matches_reference(name):
+    from sparrowpy_b200 import pyfar_shim as pf
+    g = load_golden(name)
+    rad = run_class(g)
+    n = rad.n_patches
+    vis_ref = np.unpackbits(g["visibility"])[:n * n].reshape(n, n).astype(bool)
+    assert np.array_equal(rad.visibility_matrix, vis_ref)
+    assert rad._visibility_matrix.dtype == bool
+    assert np.array_equal(rad._visible_patches, g["visible_patches"])
+    assert rad._visible_patches.dtype == np.int32
+    p = g["visible_patches"]
+    assert rel_err(rad.form_factors[p[:, 0], p[:, 1]], g["ff_pairs"]) < 1e-6
+    assert np.count_nonzero(rad.form_factors) == np.count_nonzero(g["ff_pairs"])
+    assert np.array_equal(rad._patch_2_brdf_outgoing_index, g["p2o"].astype(np.int64))
+    assert np.array_equal(rad._source_visibility, g["source_visibility"])
+    assert np.array_equal(rad._distance_patches_to_source, g["distance_patches_to_source"])
+    assert rel_err(rad._energy_init_source, g["energy_init_source"]) < 1e-6
+    tilde = rad._form_factors_tilde
+    if "tilde" in g:
+        assert tilde.shape == g["tilde"].shape
+        assert rel_err(tilde, g["tilde"]) < 1e-6
+    else:
+        assert rel_err(tilde[g["tilde_rows"]], g["tilde_sample"]) < 1e-6
+    etc = rad._energy_exchange_etc
+    assert etc.shape == tuple(g["etc_shape"])
+    if "etc" in g:
+        assert rel_err(etc, g["etc"]) < 1e-6
+    else:
+        assert rel_err(etc[g["etc_rows"]], g["etc_sample"]) < 1e-6
+    assert rel_err(etc.sum(-1), g["etc_patch_sums"]) < 1e-6
+    rcv = pf.Coordinates.from_cartesian(g["receivers"])
+    mono = rad.collect_energy_receiver_mono(rcv)
+    assert mono.time.shape == g["etc_receiver_mono"].shape
+    for r in range(mono.time.shape[0]):
+        for b in range(mono.time.shape[1]):
+            assert rel_err(mono.time[r, b], g["etc_receiver_mono"][r, b]) < 1e-6
+    assert np.allclose(mono.times, np.arange(etc.shape[-1]) * float(g["dt"]))
+    pw = rad.collect_energy_receiver_patchwise(rcv)
+    assert pw.time.shape == (len(g["receivers"]), n, etc.shape[2], etc.shape[3])
+    assert rel_err(pw.time.sum(-1), g["etc_receiver_patch_sums"]) < 1e-6
+    # order 0 / recalculate semantics (RadiosityFast.py:547-555)
+    rad.calculate_energy_exchange(float(g["speed_of_sound"]), float(g["dt"]),
+                                  float(g["duration"]), max_reflection_order=0)
+    assert rel_err(rad._energy_exchange_etc.sum(-1), g["etc_patch_sums"]) < 1e-6  # cached
+    rad.calculate_energy_exchange(float(g["speed_of_sound"]), float(g["dt"]),
+                                  float(g["duration"]), max_reflection_order=0,
+                                  recalculate=True)
+    assert rel_err(rad._energy_exchange_etc.sum(-1), g["etc_order0_sums"]) < 1e-6
+
+
+def test_f32_histograms_within_1e4():
+    from sparrowpy_b200 import pyfar_shim as pf
+    g = load_golden("scene_directional")
+    rad = run_class(g, dtype="f32")
+    assert rel_err(rad._energy_exchange_etc[g["etc_rows"]], g["etc_sample"]) < 1e-4
+    mono = rad.collect_energy_receiver_mono(pf.Coordinates.from_cartesian(g["receivers"]))
+    for r in range(mono.time.shape[0]):
+        for b in range(mono.time.shape[1]):
+            assert rel_err(mono.time[r, b], g["etc_receiver_mono"][r, b]) < 1e-4
+
+
+def test_reference_cube_visibility_pattern():
+    """reference tests/test_DRadiosityFast.py:19-29"""
+    import sparrowpy_b200 as sp
+    rad = sp.DirectionalRadiosityFast.from_polygon(sp.testing.shoebox_room_stub(1, 1, 1), 0.5)
+    rad.bake_geometry()
+    np.testing.assert_array_equal(rad._visibility_matrix[:4, :4], False)
+    np.testing.assert_array_equal(rad._visibility_matrix[:4, 4:], True)
+    np.testing.assert_array_equal(rad._visibility_matrix[4:8, 4:8], False)
+    np.testing.assert_array_equal(rad._visibility_matrix[4:8, 8:], True)
+    # upper triangle only: 6 walls x 4 patches, same-wall pairs invisible
+    assert np.sum(rad._visibility_matrix) == (24 * 24 - 6 * 16) // 2
+    assert rad._visibility_matrix.shape == (24, 24)
+    # row sums of the full (both triangles) form factor matrix ~ 1
+    # (reference tests/test_universal_formfactor.py:140-157)
+    ff = rad.form_factors
+    area = rad.patches_area
+    full = ff + (ff * area[:, None] / area[None, :]).T
+    np.testing.assert_allclose(full.sum(axis=1), 1.0, atol=1e-2)
+
+
+def test_diffuse_tilde_equals_form_factors():
+    """reference tests/test_DRadiosityFast_order.py:20-46"""
+    import sparrowpy_b200 as sp
+    rad = sp.DirectionalRadiosityFast.from_polygon(sp.testing.shoebox_room_stub(2, 2, 2), 1.0)
+    rad.bake_geometry()
+    ff = rad.form_factors
+    tilde = rad._form_factors_tilde[:, :, 0, 0]
+    iu = np.triu_indices(rad.n_patches, 1)
+    np.testing.assert_allclose(tilde[iu], ff[iu], rtol=1e-12)
+    area = rad.patches_area
+    np.testing.assert_allclose(tilde.T[iu], (ff * area[:, None] / area[None, :])[iu], rtol=1e-12)

@@ -192,10 +192,13 @@ def main():
     ap.add_argument("--config", default=os.environ.get("SPB_BENCH_CONFIG", "c2"),
                     choices=sorted(CONFIGS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--gather", default=os.environ.get("SPB_GATHER", "tma"),
+                    choices=["tma", "csr"], help="stage-1 kernel: TMA-staged tiles or CSR")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    os.environ["SPB_GATHER"] = args.gather
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -247,9 +250,14 @@ def main():
         c32, sp = _lib.I32(t.dtype), _lib.stream_ptr()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(st)
-        _lib.call("spb_exchange_gather", prev, sx.g, t.seg_ptr, t.src, t.wgt, t.dly,
-                  t.n_patches, t.n_classes, t.n_bands, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld,
-                  sx.pad, c32, sp)
+        if args.gather == "tma":
+            _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
+                      t.n_patches, t.n_classes, t.n_bands, sx.j_lo, sx.j_hi, sx.t_pad,
+                      sx.ld, sx.pad, c32, sp)
+        else:
+            _lib.call("spb_exchange_gather", prev, sx.g, t.seg_ptr, t.src, t.wgt, t.dly,
+                      t.n_patches, t.n_classes, t.n_bands, sx.j_lo, sx.j_hi, sx.t_pad,
+                      sx.ld, sx.pad, c32, sp)
         ev1.record(st)
         gather_events.append((ev0, ev1))
         _lib.call("spb_exchange_mix", sx.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
@@ -304,10 +312,12 @@ def main():
     gather_avg_ms = float(np.mean(gather_ms)) if gather_ms else float("nan")
     achieved = alg_bytes_launch / (gather_avg_ms * 1e-3) / 1e9
     # executed FMAs of the factored kernel: directed pairs x B x T_pad per order
+    # (tiled kernel: one FMA row per non-empty record slot = per kept directed pair)
     fma_launch = float(tables.src.numel()) * share * n_band * sx.t_pad
     fma_tflops = 2.0 * fma_launch / (gather_avg_ms * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "kernel": "k_gather",
+                "frac": achieved / hbm_peak, "traffic": None,
+                "kernel": "k_gather_tma" if args.gather == "tma" else "k_gather",
                 "peak_source": peak_src, "avg_launch_ms": gather_avg_ms,
                 "launches_timed": len(gather_ms),
                 "share_of_step": sum(gather_ms) / max(elapsed_ms, 1e-9),
@@ -364,6 +374,7 @@ def main():
             "config": {"workload": cfg["desc"], "name": args.config,
                        "n_patches": rad.n_patches, "visible_pairs": n_pairs,
                        "directed_pairs_kept": int(tables.src.numel()),
+                       "tile_records": int(tables.n_records), "gather": args.gather,
                        "n_directions": n_dir, "n_bands": n_band, "n_samples": n_samples,
                        "reflection_orders": orders,
                        "exchanges_per_etc": x_per_step,

@@ -61,8 +61,8 @@ int spb_device_info(int *sm_count, int *cc_major, int *cc_minor);
  *     E_cur[j,d,b,t] = sum_c coef[c,d,b] * G[c,j,b,t];   E_total += E_cur
  * ------------------------------------------------------------------------- */
 
-/* Tile geometry the kernels expect: T_pad (multiple of the time tile) and PAD
- * (>= max_delay, multiple of 32).  LD = PAD + T_pad. */
+/* Tile geometry the kernels expect: T_pad (multiple of the 256-bin time tile) and
+ * PAD (multiple of 32, > max_delay + 32).  LD = PAD + T_pad. */
 int spb_exchange_layout(int64_t n_samples, int64_t max_delay, int dtype,
                         int64_t *t_pad, int64_t *pad);
 
@@ -84,6 +84,21 @@ int spb_exchange_gather(const void *e_prev, void *g, const int64_t *seg_ptr,
                         int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
                         int64_t pad, int dtype, void *stream);
 
+/* Stage 1 with TMA-staged energy tiles (the fast path).  Same result as
+ * spb_exchange_gather; the pair list is stored per tile of R neighbouring receivers
+ * (R, the delay bucket and the record size come from spb_tile_geometry) as the union
+ * of the tile's senders: tile = class * ceil(N/R) + j / R owns records
+ * ent_ptr[tile] .. ent_ptr[tile+1]; a record is
+ *     { dtype w[R]; uint8 rel[R]; int32 src; int32 dmin; }
+ * = weights and (delay - dmin) of the R receivers for sender row src, dmin a multiple
+ * of the bucket.  j_lo must be a multiple of R. */
+int spb_tile_geometry(int dtype, int64_t *receivers_per_tile, int64_t *delay_bucket,
+                      int64_t *record_bytes);
+int spb_exchange_gather_tiled(const void *e_prev, void *g, const int64_t *ent_ptr,
+                              const void *recs, int64_t n_patches, int64_t n_classes,
+                              int64_t n_bands, int64_t j_lo, int64_t j_hi, int64_t t_pad,
+                              int64_t ld, int64_t pad, int dtype, void *stream);
+
 /* Stage 2 of one order for receiver patches [j_lo, j_hi): BRDF contraction,
  * writes e_cur rows of those patches and accumulates them into e_total.
  * coef: [C, D, B] in dtype. */
@@ -94,11 +109,13 @@ int spb_exchange_mix(const void *g, void *e_cur, void *e_total,
                      int64_t pad, int dtype, void *stream);
 
 /* `_energy_exchange` (RadiosityFast.py:1073-1145) on one GPU: init + max_order
- * x (gather, mix).  e_a, e_b: ping-pong [N*D*B, LD]; g: [C*N*B, LD].
+ * x (gather, mix).  e_a, e_b: ping-pong [N*D*B, LD]; g: [C*N*B, LD].  With recs != 0
+ * stage 1 is the tiled TMA kernel, otherwise the CSR kernel.
  * max_order < 1 means "initial energy only" (RadiosityFast.py:550-555, :1119). */
 int spb_energy_exchange(const void *e0, const int32_t *delay0,
                         const int64_t *seg_ptr, const int32_t *src, const void *wgt,
-                        const int32_t *dly, const void *coef, int64_t n_patches,
+                        const int32_t *dly, const int64_t *ent_ptr, const void *recs,
+                        const void *coef, int64_t n_patches,
                         int64_t n_classes, int64_t n_dirs, int64_t n_bands,
                         int64_t n_samples, int64_t t_pad, int64_t pad,
                         int64_t max_order, void *e_total, void *e_a, void *e_b,

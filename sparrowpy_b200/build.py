@@ -20,6 +20,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
 # rounding model bit for bit: no FMA contraction there (explicit fma() only).
 SOURCES = [
     ("exchange.cu", []),
+    ("exchange_tma.cu", []),
     ("bake.cu", ["--fmad=false"]),
 ]
 

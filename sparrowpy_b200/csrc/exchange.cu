@@ -258,7 +258,9 @@ int spb_exchange_layout(int64_t n_samples, int64_t max_delay, int dtype, int64_t
     SPB_REQUIRE(n_samples > 0 && max_delay >= 0, "n_samples > 0, max_delay >= 0");
     SPB_REQUIRE(dtype == SPB_F64 || dtype == SPB_F32, "dtype");
     *t_pad = round_up(n_samples, kTimeTile);
-    *pad = round_up(max_delay > 0 ? max_delay : 1, 32);
+    // one spare 32-bin bucket in front: the tiled gather stages windows that start
+    // 32 bins before the delay bucket of a record (exchange_tma.cu)
+    *pad = round_up(max_delay + 1, 32) + 32;
     return 0;
 }
 
@@ -312,7 +314,8 @@ int spb_exchange_mix(const void *g, void *e_cur, void *e_total, const int64_t *s
 
 int spb_energy_exchange(const void *e0, const int32_t *delay0, const int64_t *seg_ptr,
                         const int32_t *src, const void *wgt, const int32_t *dly,
-                        const void *coef, int64_t n_patches, int64_t n_classes,
+                        const int64_t *ent_ptr, const void *recs, const void *coef,
+                        int64_t n_patches, int64_t n_classes,
                         int64_t n_dirs, int64_t n_bands, int64_t n_samples,
                         int64_t t_pad, int64_t pad, int64_t max_order, void *e_total,
                         void *e_a, void *e_b, void *g, int dtype, void *stream) {
@@ -328,8 +331,13 @@ int spb_energy_exchange(const void *e0, const int32_t *delay0, const int64_t *se
     SPB_CUDA(cudaMemsetAsync(e_b, 0, esz * n_patches * db * ld, (cudaStream_t)stream));
     void *prev = e_a, *cur = e_b;
     for (int64_t k = 0; k < max_order; ++k) {
-        rc = spb_exchange_gather(prev, g, seg_ptr, src, wgt, dly, n_patches, n_classes,
-                                 n_bands, 0, n_patches, t_pad, ld, pad, dtype, stream);
+        if (recs)
+            rc = spb_exchange_gather_tiled(prev, g, ent_ptr, recs, n_patches, n_classes,
+                                           n_bands, 0, n_patches, t_pad, ld, pad, dtype,
+                                           stream);
+        else
+            rc = spb_exchange_gather(prev, g, seg_ptr, src, wgt, dly, n_patches, n_classes,
+                                     n_bands, 0, n_patches, t_pad, ld, pad, dtype, stream);
         if (rc) return rc;
         rc = spb_exchange_mix(g, cur, e_total, seg_ptr, coef, n_patches, n_classes,
                               n_dirs, n_bands, 0, n_patches, t_pad, ld, pad, dtype, stream);

@@ -12,6 +12,8 @@ The histogram buffers are allocated for ``world * S`` patches so that every shar
 has the same number of rows (NCCL all-gather needs equal counts); the padding
 patches own no pairs and stay zero.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -19,9 +21,13 @@ from . import _lib
 from .exchange import EnergyHistogram
 
 
+SHARD_ALIGN = 8
+
+
 def shard_range(n_patches, rank, world):
     """Receiver patches owned by ``rank``: (j_lo, j_hi, shard_size)."""
     size = -(-n_patches // world)
+    size = -(-size // SHARD_ALIGN) * SHARD_ALIGN     # tiles of 8 receivers stay whole
     lo = min(n_patches, rank * size)
     hi = min(n_patches, lo + size)
     return lo, hi, size
@@ -64,9 +70,14 @@ class ShardedExchange:
         t = self.t
         code = _lib.I32(t.dtype)
         st = _lib.stream_ptr()
-        _lib.call("spb_exchange_gather", prev, self.g, t.seg_ptr, t.src, t.wgt, t.dly,
-                  t.n_patches, t.n_classes, t.n_bands, self.j_lo, self.j_hi, self.t_pad,
-                  self.ld, self.pad, code, st)
+        if t.recs is not None and os.environ.get("SPB_GATHER", "tma") != "csr":
+            _lib.call("spb_exchange_gather_tiled", prev, self.g, t.ent_ptr, t.recs,
+                      t.n_patches, t.n_classes, t.n_bands, self.j_lo, self.j_hi, self.t_pad,
+                      self.ld, self.pad, code, st)
+        else:
+            _lib.call("spb_exchange_gather", prev, self.g, t.seg_ptr, t.src, t.wgt, t.dly,
+                      t.n_patches, t.n_classes, t.n_bands, self.j_lo, self.j_hi,
+                      self.t_pad, self.ld, self.pad, code, st)
         _lib.call("spb_exchange_mix", self.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
                   t.n_classes, t.n_dirs, t.n_bands, self.j_lo, self.j_hi, self.t_pad,
                   self.ld, self.pad, code, st)

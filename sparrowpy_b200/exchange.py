@@ -7,6 +7,7 @@ include/sparrow_b200.h.  PyTorch is used for device memory, streams and index
 bookkeeping only; all arithmetic on the energy histograms runs in the CUDA
 kernels of csrc/exchange.cu.
 """
+import os
 from dataclasses import dataclass
 
 import torch
@@ -29,6 +30,9 @@ class PairTables:
     max_delay: int
     n_directed: int            # directed pairs before dropping delay >= T
     dtype: int
+    ent_ptr: torch.Tensor = None   # (C*ceil(N/R) + 1,) int64  tiled records (TMA path)
+    recs: torch.Tensor = None      # (n_records, record_bytes) uint8
+    n_records: int = 0
 
 
 def directed_pairs(pairs, ff_pairs, areas):
@@ -67,13 +71,85 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     seg_ptr[1:] = torch.cumsum(counts, 0)
     src = (sender[order] * n_dirs + out_dir[order].long()).to(torch.int32)
     max_delay = int(delay.max().item()) if delay.numel() else 0
+    ent_ptr, recs = build_tile_records(sender, receiver, ff, delay, out_dir, cls, n_patches,
+                                       n_dirs, n_classes, code)
     return PairTables(
+        ent_ptr=ent_ptr, recs=recs, n_records=int(recs.shape[0]),
         seg_ptr=seg_ptr.contiguous(), src=src.contiguous(),
         wgt=ff[order].to(tdt).contiguous(),
         dly=delay[order].to(torch.int32).contiguous(),
         coef=coef.to(tdt).contiguous(), n_patches=int(n_patches),
         n_classes=int(n_classes), n_dirs=int(n_dirs), n_bands=int(n_bands),
         max_delay=max_delay, n_directed=n_directed, dtype=code)
+
+
+def tile_geometry(code):
+    """(receivers per tile, delay bucket, record bytes) of the tiled gather kernel."""
+    import ctypes
+    lib = _lib.load()
+    r, q, nbytes = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = lib.spb_tile_geometry(ctypes.c_int(code), ctypes.byref(r), ctypes.byref(q),
+                               ctypes.byref(nbytes))
+    if rc != 0:
+        raise _lib.SparrowB200Error(lib.spb_last_error().decode())
+    return r.value, q.value, nbytes.value
+
+
+def build_tile_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs,
+                       n_classes, code):
+    """Union-of-senders records for the TMA-staged gather (csrc/exchange_tma.cu).
+
+    A tile is R neighbouring receivers of one class; directed pairs that share the
+    tile, the sender row and the 32-bin delay bucket are merged into one record
+    ``{w[R], rel[R], src, dmin}``.  Pure index bookkeeping (sort / unique / scatter).
+    """
+    n_r, bucket, rec_bytes = tile_geometry(code)
+    tdt = _lib.torch_dtype(code)
+    dev = sender.device
+    n_blocks = -(-n_patches // n_r)
+    n_tiles = n_classes * n_blocks
+    if sender.numel() == 0:
+        return (torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev),
+                torch.zeros((0, rec_bytes), dtype=torch.uint8, device=dev))
+    n_rows = n_patches * n_dirs
+    tile = cls.long() * n_blocks + receiver.long() // n_r
+    slot = receiver.long() % n_r
+    srow = sender.long() * n_dirs + out_dir.long()
+    bkt = delay.long() // bucket
+    n_bkt = int(bkt.max().item()) + 1
+    key = (tile * n_rows + srow) * n_bkt + bkt
+    uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
+    n_rec = uniq.numel()
+    w = torch.zeros((n_rec, n_r), dtype=tdt, device=dev)
+    w[inv, slot] = ff.to(tdt)
+    # shift (delay - dmin) per slot; -1 marks an empty slot for the passes below
+    shift = torch.full((n_rec, n_r), -1, dtype=torch.int16, device=dev)
+    shift[inv, slot] = (delay.long() - bkt * bucket).to(torch.int16)
+    # reload mask: bit s set when slot s is occupied and its shift differs from the
+    # shift the kernel has loaded (that of the previous occupied slot); empty slots
+    # repeat the previous shift so that they never trigger a reload
+    mask = torch.zeros(n_rec, dtype=torch.int64, device=dev)
+    cur = torch.full((n_rec,), -1, dtype=torch.int16, device=dev)
+    rel = torch.zeros((n_rec, n_r), dtype=torch.uint8, device=dev)
+    for s_ in range(n_r):
+        col = shift[:, s_]
+        present = col >= 0
+        change = present & (col != cur)
+        mask |= change.long() << s_
+        cur = torch.where(present, col, cur)
+        rel[:, s_] = torch.clamp(cur, min=0).to(torch.uint8)
+    dmin = (uniq % n_bkt) * bucket
+    assert int(dmin.max().item()) < (1 << 24)
+    packed = dmin | (mask << 24)
+    packed = torch.where(packed >= (1 << 31), packed - (1 << 32), packed)   # as int32 bits
+    meta = torch.stack([(uniq // n_bkt) % n_rows, packed], dim=1).to(torch.int32)
+    recs = torch.cat([w.view(torch.uint8), rel, meta.contiguous().view(torch.uint8)],
+                     dim=1).contiguous()
+    assert recs.shape[1] == rec_bytes, (recs.shape, rec_bytes)
+    counts = torch.bincount(uniq // (n_bkt * n_rows), minlength=n_tiles)
+    ent_ptr = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
+    ent_ptr[1:] = torch.cumsum(counts, 0)
+    return ent_ptr.contiguous(), recs
 
 
 class EnergyHistogram:
@@ -127,7 +203,9 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
     ws = workspace or ExchangeWorkspace(t, n_samples, device, need_orders=max_order >= 1)
     e0 = e0.to(tdt).contiguous()
     delay0 = delay0.to(torch.int32).contiguous()
-    _lib.call("spb_energy_exchange", e0, delay0, t.seg_ptr, t.src, t.wgt, t.dly, t.coef,
+    use_tiles = t.recs is not None and os.environ.get("SPB_GATHER", "tma") != "csr"
+    _lib.call("spb_energy_exchange", e0, delay0, t.seg_ptr, t.src, t.wgt, t.dly,
+              t.ent_ptr if use_tiles else None, t.recs if use_tiles else None, t.coef,
               t.n_patches, t.n_classes, t.n_dirs, t.n_bands, n_samples, ws.t_pad, ws.pad,
               int(max_order), ws.e_total, ws.e_a, ws.e_b, ws.g, _lib.I32(t.dtype),
               _lib.stream_ptr())

@@ -53,10 +53,12 @@ def device_tables(g, out, dtype, n_samples):
                                       n, n_samples, dtype)
 
 
+@pytest.mark.parametrize("gather", ["tma", "csr"])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("name", SCENES)
-def test_exchange_matches_oracle(oracle, name, dtype):
+def test_exchange_matches_oracle(oracle, name, dtype, gather, monkeypatch):
     from sparrowpy_b200 import exchange
+    monkeypatch.setenv("SPB_GATHER", gather)
     g = load_golden(name)
     out = oracle_run(oracle, g)
     etc_ref = out["etc"]
@@ -130,3 +132,55 @@ def test_exchange_linearity_and_empty(oracle):
     h = exchange.energy_exchange(empty, e0, delay0, n_samples, 4).dense()
     h0 = exchange.energy_exchange(tables, e0, delay0, n_samples, 0).dense()
     assert torch.equal(h, h0)
+
+
+def test_tiled_and_csr_gather_agree_on_ragged_lists():
+    """Random sparse pair lists (empty segments, delays across bucket borders,
+    N not a multiple of the receiver tile): both stage-1 kernels give the same G."""
+    from sparrowpy_b200 import _lib, exchange
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    n, d, b, c, t_len = 53, 3, 2, 4, 300
+    m = 4000
+    sender = torch.randint(0, n, (m,), generator=gen)
+    receiver = torch.randint(0, n, (m,), generator=gen)
+    key = sender * n + receiver
+    _, first = np.unique(key.numpy(), return_index=True)      # one pair per (i, j)
+    sel = torch.from_numpy(np.sort(first))
+    sender, receiver = sender[sel].to(dev), receiver[sel].to(dev)
+    m = sender.numel()
+    ff = torch.rand(m, generator=gen, dtype=torch.float64).to(dev)
+    delay = torch.randint(0, 140, (m,), generator=gen).to(dev)
+    delay[::7] = 31 + (delay[::7] % 3)                        # straddle the bucket border
+    out_dir = torch.randint(0, d, (m,), generator=gen).to(dev)
+    cls = torch.randint(0, c, (m,), generator=gen).to(dev)
+    cls[receiver % 5 == 0] = 1                                # leave some segments empty
+    coef = torch.rand((c, d, b), generator=gen, dtype=torch.float64).to(dev)
+    tables = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n,
+                                        t_len, "f64")
+    t_pad, pad = _lib.exchange_layout(t_len, tables.max_delay, tables.dtype)
+    ld = t_pad + pad
+    prev = torch.zeros((n * d * b, ld), dtype=torch.float64, device=dev)
+    prev[:, pad:pad + t_len] = torch.rand((n * d * b, t_len), generator=gen,
+                                          dtype=torch.float64).to(dev)
+    g1 = torch.zeros((c * n * b, ld), dtype=torch.float64, device=dev)
+    g2 = torch.zeros_like(g1)
+    st, code = _lib.stream_ptr(), _lib.I32(tables.dtype)
+    _lib.call("spb_exchange_gather", prev, g1, tables.seg_ptr, tables.src, tables.wgt,
+              tables.dly, n, c, b, 0, n, t_pad, ld, pad, code, st)
+    _lib.call("spb_exchange_gather_tiled", prev, g2, tables.ent_ptr, tables.recs, n, c, b,
+              0, n, t_pad, ld, pad, code, st)
+    torch.cuda.synchronize()
+    a, bb = g1[:, pad:pad + t_len], g2[:, pad:pad + t_len]
+    assert torch.allclose(a, bb, rtol=1e-12, atol=1e-14)
+    assert a.abs().max() > 0
+    # brute-force check of one non-empty segment
+    seg = int(torch.nonzero(tables.seg_ptr[1:] - tables.seg_ptr[:-1])[0])
+    cc, jj = seg // n, seg % n
+    sel = (cls == cc) & (receiver == jj) & (delay < t_len)
+    ref = torch.zeros(t_len, dtype=torch.float64, device=dev)
+    for q in torch.nonzero(sel).reshape(-1).tolist():
+        row = (int(sender[q]) * d + int(out_dir[q])) * b + 1
+        dl = int(delay[q])
+        ref[dl:] += ff[q] * prev[row, pad:pad + t_len - dl]
+    assert torch.allclose(g2[(seg * b) + 1, pad:pad + t_len], ref, rtol=1e-12, atol=1e-14)

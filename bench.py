@@ -245,24 +245,25 @@ def main():
     st = torch.cuda.current_stream()
     gather_events = []
 
-    def timed_order(prev, cur, total):
+    def timed_order(prev, cur, total, b_lo, b_hi):
         t = sx.t
         c32, sp = _lib.I32(t.dtype), _lib.stream_ptr()
+        cst = torch.cuda.current_stream()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(st)
+        ev0.record(cst)
         if args.gather == "tma":
             _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
-                      t.n_patches, t.n_classes, t.n_bands, sx.j_lo, sx.j_hi, sx.t_pad,
-                      sx.ld, sx.pad, c32, sp)
+                      t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
+                      sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32, sp)
         else:
             _lib.call("spb_exchange_gather", prev, sx.g, t.seg_ptr, t.src, t.wgt, t.dly,
-                      t.n_patches, t.n_classes, t.n_bands, sx.j_lo, sx.j_hi, sx.t_pad,
-                      sx.ld, sx.pad, c32, sp)
-        ev1.record(st)
+                      t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
+                      sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32, sp)
+        ev1.record(cst)
         gather_events.append((ev0, ev1))
         _lib.call("spb_exchange_mix", sx.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
-                  t.n_classes, t.n_dirs, t.n_bands, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld,
-                  sx.pad, c32, sp)
+                  sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, sx.j_lo, sx.j_hi,
+                  sx.t_pad, sx.ld, sx.pad, c32, sp)
 
     sx.compute = timed_order
 
@@ -279,7 +280,9 @@ def main():
         step()
     barrier()
     gather_events.clear()
-    launches_per_step = orders * 2 + 4          # gather+mix per order, init (memsets+scatter)
+    # gather+mix per (order, band launch) + init (memsets + scatter)
+    band_launches = n_band if world > 1 else 1
+    launches_per_step = orders * band_launches * 2 + 4
     with ClockSampler(local_rank) as clocks:
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -308,12 +311,13 @@ def main():
     share = (sx.j_hi - sx.j_lo) / max(rad.n_patches, 1)
     # algorithmic bytes per pair.bin exchange = B*(1+2D)*sizeof; one gather
     # launch processes this rank's directed pairs x T bins of one order
-    alg_bytes_launch = 2.0 * n_pairs * share * n_samples * n_band * (1 + 2 * n_dir) * esize
+    alg_bytes_launch = (2.0 * n_pairs * share * n_samples * n_band * (1 + 2 * n_dir) * esize
+                        / band_launches)
     gather_avg_ms = float(np.mean(gather_ms)) if gather_ms else float("nan")
     achieved = alg_bytes_launch / (gather_avg_ms * 1e-3) / 1e9
     # executed FMAs of the factored kernel: directed pairs x B x T_pad per order
     # (tiled kernel: one FMA row per non-empty record slot = per kept directed pair)
-    fma_launch = float(tables.src.numel()) * share * n_band * sx.t_pad
+    fma_launch = float(tables.src.numel()) * share * n_band * sx.t_pad / band_launches
     fma_tflops = 2.0 * fma_launch / (gather_avg_ms * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None,

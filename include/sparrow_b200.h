@@ -18,9 +18,11 @@
  *     message of the calling thread's last failure;
  *   - dtype: SPB_F64 = 0 (reference precision), SPB_F32 = 1 (histograms in fp32).
  *
- * Energy histogram layout in HBM ("padded rows"):
- *   E[row][PAD + t],  row = (patch * D + direction) * B + band,
- *   row stride LD = PAD + T_pad elements.  The PAD leading elements of every row
+ * Energy histogram layout in HBM ("padded rows", band-major):
+ *   E[row][PAD + t],  row = (band * n_alloc + patch) * D + direction,
+ *   row stride LD = PAD + T_pad elements.  Bands are independent through the whole
+ *   recursion, so each band is one contiguous block (per-band all-gathers can
+ *   overlap the other bands' kernels).  The PAD leading elements of every row
  *   are a zero pre-roll (t < 0), PAD >= the largest pair delay, so a delayed read
  *   E[row][PAD + t - delay] never needs a bounds test.  T_pad >= T is the tile
  *   multiple the caller got from spb_exchange_layout().
@@ -57,8 +59,8 @@ int spb_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * seg_ptr[s] .. seg_ptr[s+1].
  *
  * One reflection order = gather (stage 1) followed by mix (stage 2):
- *     G[c,j,b,t]   = sum_{q in seg(c,j)} ff_q * E_prev[src_q, b, t - dly_q]
- *     E_cur[j,d,b,t] = sum_c coef[c,d,b] * G[c,j,b,t];   E_total += E_cur
+ *     G[b,c,j,t]     = sum_{q in seg(c,j)} ff_q * E_prev[b, src_q, t - dly_q]
+ *     E_cur[b,j,d,t] = sum_c coef[c,d,b] * G[b,c,j,t];   E_total += E_cur
  * ------------------------------------------------------------------------- */
 
 /* Tile geometry the kernels expect: T_pad (multiple of the 256-bin time tile) and
@@ -67,20 +69,24 @@ int spb_exchange_layout(int64_t n_samples, int64_t max_delay, int dtype,
                         int64_t *t_pad, int64_t *pad);
 
 /* `_energy_exchange_init_energy` (RadiosityFast.py:1037-1070): zero e_total and
- * e_prev, then add e0[i,d,b] at bin delay0[i] of every row of patch i.  Energy
- * whose bin is >= n_samples is dropped (the reference writes out of bounds).
- * e0: [N, D*B]; delay0: [N] int32; e_total/e_prev: [N*D*B, LD] (e_prev may be 0). */
+ * e_prev (all n_alloc*D*B rows), then add e0[i,d,b] at bin delay0[i] of row
+ * (b, i, d).  Energy whose bin is >= n_samples is dropped (the reference writes out
+ * of bounds).  e0: [N, D, B]; delay0: [N] int32; e_prev may be 0.
+ * n_alloc >= N is the number of patches the histogram buffers are allocated for
+ * (> N only when shards are padded to equal size, see distributed.py). */
 int spb_exchange_init(void *e_total, void *e_prev, const void *e0,
-                      const int32_t *delay0, int64_t n_patches, int64_t db,
-                      int64_t n_samples, int64_t ld, int64_t pad, int dtype,
-                      void *stream);
+                      const int32_t *delay0, int64_t n_patches, int64_t n_alloc,
+                      int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
+                      int64_t pad, int dtype, void *stream);
 
-/* Stage 1 of one order for receiver patches [j_lo, j_hi) (all of them on one
- * GPU, a shard on several).  g: [C*N*B, LD], only rows of non-empty segments in
- * the range are written.  seg_ptr: [C*N + 1] int64; src, dly: int32; wgt: dtype. */
+/* Stage 1 of one order for receiver patches [j_lo, j_hi) and bands [b_lo, b_hi)
+ * (everything on one GPU; a receiver shard, or one band of a pipelined schedule, on
+ * several).  g: [B, C*N, LD], only rows of non-empty segments in the range are
+ * written.  seg_ptr: [C*N + 1] int64; src, dly: int32; wgt: dtype.  CSR kernel. */
 int spb_exchange_gather(const void *e_prev, void *g, const int64_t *seg_ptr,
                         const int32_t *src, const void *wgt, const int32_t *dly,
-                        int64_t n_patches, int64_t n_classes, int64_t n_bands,
+                        int64_t n_patches, int64_t n_alloc, int64_t n_classes,
+                        int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi,
                         int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
                         int64_t pad, int dtype, void *stream);
 
@@ -89,59 +95,62 @@ int spb_exchange_gather(const void *e_prev, void *g, const int64_t *seg_ptr,
  * (R, the delay bucket and the record size come from spb_tile_geometry) as the union
  * of the tile's senders: tile = class * ceil(N/R) + j / R owns records
  * ent_ptr[tile] .. ent_ptr[tile+1]; a record is
- *     { dtype w[R]; uint8 rel[R]; int32 src; int32 dmin; }
- * = weights and (delay - dmin) of the R receivers for sender row src, dmin a multiple
- * of the bucket.  j_lo must be a multiple of R. */
+ *     { dtype w[R]; uint8 rel[R]; int32 src; int32 dmin_and_mask; }
+ * = weights and (delay - dmin) of the R receivers for sender row src; dmin (low 24
+ * bits, a multiple of the bucket) and a reload mask (high 8 bits: slot s starts a
+ * new shift; empty slots have w = 0 and repeat the previous shift).  j_lo must be a
+ * multiple of R. */
 int spb_tile_geometry(int dtype, int64_t *receivers_per_tile, int64_t *delay_bucket,
                       int64_t *record_bytes);
 int spb_exchange_gather_tiled(const void *e_prev, void *g, const int64_t *ent_ptr,
-                              const void *recs, int64_t n_patches, int64_t n_classes,
-                              int64_t n_bands, int64_t j_lo, int64_t j_hi, int64_t t_pad,
-                              int64_t ld, int64_t pad, int dtype, void *stream);
+                              const void *recs, int64_t n_patches, int64_t n_alloc,
+                              int64_t n_classes, int64_t n_dirs, int64_t n_bands,
+                              int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi,
+                              int64_t t_pad, int64_t ld, int64_t pad, int dtype,
+                              void *stream);
 
-/* Stage 2 of one order for receiver patches [j_lo, j_hi): BRDF contraction,
- * writes e_cur rows of those patches and accumulates them into e_total.
- * coef: [C, D, B] in dtype. */
+/* Stage 2 of one order for receiver patches [j_lo, j_hi), bands [b_lo, b_hi): BRDF
+ * contraction, writes e_cur rows of those patches and accumulates them into
+ * e_total.  coef: [C, D, B] in dtype. */
 int spb_exchange_mix(const void *g, void *e_cur, void *e_total,
                      const int64_t *seg_ptr, const void *coef, int64_t n_patches,
-                     int64_t n_classes, int64_t n_dirs, int64_t n_bands,
-                     int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
-                     int64_t pad, int dtype, void *stream);
+                     int64_t n_alloc, int64_t n_classes, int64_t n_dirs, int64_t n_bands,
+                     int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi,
+                     int64_t t_pad, int64_t ld, int64_t pad, int dtype, void *stream);
 
 /* `_energy_exchange` (RadiosityFast.py:1073-1145) on one GPU: init + max_order
- * x (gather, mix).  e_a, e_b: ping-pong [N*D*B, LD]; g: [C*N*B, LD].  With recs != 0
+ * x (gather, mix).  e_a, e_b: ping-pong [B*N*D, LD]; g: [B*C*N, LD].  With recs != 0
  * stage 1 is the tiled TMA kernel, otherwise the CSR kernel.
  * max_order < 1 means "initial energy only" (RadiosityFast.py:550-555, :1119). */
 int spb_energy_exchange(const void *e0, const int32_t *delay0,
                         const int64_t *seg_ptr, const int32_t *src, const void *wgt,
                         const int32_t *dly, const int64_t *ent_ptr, const void *recs,
-                        const void *coef, int64_t n_patches,
-                        int64_t n_classes, int64_t n_dirs, int64_t n_bands,
-                        int64_t n_samples, int64_t t_pad, int64_t pad,
-                        int64_t max_order, void *e_total, void *e_a, void *e_b,
-                        void *g, int dtype, void *stream);
+                        const void *coef, int64_t n_patches, int64_t n_classes,
+                        int64_t n_dirs, int64_t n_bands, int64_t n_samples,
+                        int64_t t_pad, int64_t pad, int64_t max_order, void *e_total,
+                        void *e_a, void *e_b, void *g, int dtype, void *stream);
 
 /* ---------------------------------------------------------------------------
  * Receiver collection (reference RadiosityFast.py:686-752 `_collect_energy_patches`
  * + :1148-1185 `_collect_receiver_energy`):
- *   out[r,b,(t + shift[r,k]) mod T] += e_total[k, rdir[r,k], b, t] * scale[r,k,b]
+ *   out[r,b,(t + shift[r,k]) mod T] += e_total[b, k, rdir[r,k], t] * scale[r,k,b]
  * scale = patch->receiver factor * exp(-air[b]*dist), shift = ceil-delay mod T
  * (the reference's np.roll is circular).  mono: [R, B, T] dense (no padding).
  * partial: scratch [n_split, R, B, T].
  * ------------------------------------------------------------------------- */
 int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *shift,
                      const void *scale, int64_t n_receivers, int64_t n_patches,
-                     int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
-                     int64_t pad, void *mono, void *partial, int64_t n_split,
+                     int64_t n_alloc, int64_t n_dirs, int64_t n_bands, int64_t n_samples,
+                     int64_t ld, int64_t pad, void *mono, void *partial, int64_t n_split,
                      int dtype, void *stream);
 
 /* patch-wise variant (`collect_energy_receiver_patchwise`, RadiosityFast.py:660):
  * out: [R, N, B, T] dense. */
 int spb_collect_patchwise(const void *e_total, const int32_t *rdir,
                           const int32_t *shift, const void *scale,
-                          int64_t n_receivers, int64_t n_patches, int64_t n_dirs,
-                          int64_t n_bands, int64_t n_samples, int64_t ld, int64_t pad,
-                          void *out, int dtype, void *stream);
+                          int64_t n_receivers, int64_t n_patches, int64_t n_alloc,
+                          int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
+                          int64_t pad, void *out, int dtype, void *stream);
 
 /* ---------------------------------------------------------------------------
  * Geometry baking.  All coordinates are FP64 (the reference's dtype); boolean and

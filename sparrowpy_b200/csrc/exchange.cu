@@ -19,17 +19,23 @@ constexpr int kTimeTile = 32 * kChunks;    // 256 time bins per warp
 // ---------------------------------------------------------------------------
 // initial energy: RadiosityFast.py:1037-1070
 // ---------------------------------------------------------------------------
+// e0 is (patch, direction, band); histogram rows are band-major:
+// row(b, patch, dir) = (b * n_alloc + patch) * D + dir
 template <typename T>
 __global__ void k_init_scatter(T *__restrict__ e_total, T *__restrict__ e_prev,
                                const T *__restrict__ e0,
-                               const int32_t *__restrict__ delay0, int64_t n_rows,
-                               int64_t db, int64_t n_samples, int64_t ld, int64_t pad) {
-    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
-    int64_t patch = row / db;
-    int32_t d = delay0[patch];
+                               const int32_t *__restrict__ delay0, int64_t n_patches,
+                               int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
+                               int64_t n_samples, int64_t ld, int64_t pad) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_patches * n_dirs * n_bands) return;
+    const int64_t b = idx % n_bands;
+    const int64_t pd = idx / n_bands;               // patch * D + dir
+    const int64_t patch = pd / n_dirs;
+    const int32_t d = delay0[patch];
     if (d < 0 || d >= n_samples) return;   // out-of-range energy is dropped
-    T v = e0[row];
+    const T v = e0[idx];
+    const int64_t row = b * n_alloc * n_dirs + pd;
     e_total[row * ld + pad + d] += v;
     if (e_prev) e_prev[row * ld + pad + d] += v;
 }
@@ -44,15 +50,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_gather(const T *__restrict__ e_prev, T *__restrict__ g,
          const int64_t *__restrict__ seg_ptr, const int32_t *__restrict__ src,
          const T *__restrict__ wgt, const int32_t *__restrict__ dly,
-         int64_t n_patches, int64_t n_classes, int64_t n_bands, int64_t j_lo,
-         int64_t n_j, int64_t ld, int64_t pad) {
+         int64_t n_patches, int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
+         int64_t b_lo, int64_t n_b, int64_t j_lo, int64_t n_j, int64_t ld, int64_t pad) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int64_t n_local = n_classes * n_j;
     const int64_t widx = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-    if (widx >= n_local * n_bands) return;
-    const int64_t b = widx / n_local;
-    const int64_t loc = widx - b * n_local;
+    if (widx >= n_local * n_b) return;
+    const int64_t b = b_lo + widx / n_local;
+    const int64_t loc = widx % n_local;
     const int64_t c = loc / n_j;
     const int64_t seg = c * n_patches + j_lo + (loc - c * n_j);
     const int64_t p0 = seg_ptr[seg], p1 = seg_ptr[seg + 1];
@@ -62,8 +68,7 @@ k_gather(const T *__restrict__ e_prev, T *__restrict__ g,
     T acc[kChunks];
 #pragma unroll
     for (int v = 0; v < kChunks; ++v) acc[v] = T(0);
-    const T *base = e_prev + b * ld + pad + t0 + lane;
-    const int64_t row_stride = n_bands * ld;
+    const T *base = e_prev + b * n_alloc * n_dirs * ld + pad + t0 + lane;
 
     for (int64_t p = p0; p < p1; p += 32) {
         const int64_t q = p + lane;
@@ -75,12 +80,12 @@ k_gather(const T *__restrict__ e_prev, T *__restrict__ g,
             const int32_t sk = __shfl_sync(0xffffffffu, s, k);
             const int32_t dk = __shfl_sync(0xffffffffu, d, k);
             const T wk = __shfl_sync(0xffffffffu, w, k);
-            const T *row = base + (int64_t)sk * row_stride - dk;
+            const T *row = base + (int64_t)sk * ld - dk;
 #pragma unroll
             for (int v = 0; v < kChunks; ++v) acc[v] = fma(wk, row[32 * v], acc[v]);
         }
     }
-    T *out = g + (seg * n_bands + b) * ld + pad + t0 + lane;
+    T *out = g + (b * n_classes * n_patches + seg) * ld + pad + t0 + lane;
 #pragma unroll
     for (int v = 0; v < kChunks; ++v) out[32 * v] = acc[v];
 }
@@ -96,11 +101,12 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_mix(const T *__restrict__ g, T *__restrict__ e_cur, T *__restrict__ e_total,
       const int64_t *__restrict__ seg_ptr, const T *__restrict__ coef,
-      int64_t n_patches, int64_t n_classes, int64_t n_dirs, int64_t n_bands,
-      int64_t j_lo, int64_t t_pad, int64_t ld, int64_t pad) {
+      int64_t n_patches, int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
+      int64_t n_bands, int64_t b_lo, int64_t j_lo, int64_t n_j, int64_t t_pad, int64_t ld,
+      int64_t pad) {
     const int64_t jb = blockIdx.x;
-    const int64_t j = j_lo + jb / n_bands;
-    const int64_t b = jb % n_bands;
+    const int64_t b = b_lo + jb / n_j;
+    const int64_t j = j_lo + jb % n_j;
     const int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (t >= t_pad) return;
     for (int64_t d0 = 0; d0 < n_dirs; d0 += kMixDirs) {
@@ -110,7 +116,7 @@ k_mix(const T *__restrict__ g, T *__restrict__ e_cur, T *__restrict__ e_total,
         for (int64_t c = 0; c < n_classes; ++c) {
             const int64_t seg = c * n_patches + j;
             if (seg_ptr[seg] == seg_ptr[seg + 1]) continue;   // CTA-uniform
-            const T gv = g[(seg * n_bands + b) * ld + pad + t];
+            const T gv = g[(b * n_classes * n_patches + seg) * ld + pad + t];
             const T *cf = coef + (c * n_dirs + d0) * n_bands + b;
 #pragma unroll
             for (int dd = 0; dd < kMixDirs; ++dd)
@@ -119,7 +125,7 @@ k_mix(const T *__restrict__ g, T *__restrict__ e_cur, T *__restrict__ e_total,
 #pragma unroll
         for (int dd = 0; dd < kMixDirs; ++dd) {
             if (d0 + dd < n_dirs) {
-                const int64_t o = ((j * n_dirs + d0 + dd) * n_bands + b) * ld + pad + t;
+                const int64_t o = ((b * n_alloc + j) * n_dirs + d0 + dd) * ld + pad + t;
                 e_cur[o] = acc[dd];
                 e_total[o] += acc[dd];
             }
@@ -134,7 +140,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_collect_partial(const T *__restrict__ e_total, const int32_t *__restrict__ rdir,
                   const int32_t *__restrict__ shift, const T *__restrict__ scale,
-                  int64_t n_patches, int64_t n_dirs, int64_t n_bands,
+                  int64_t n_patches, int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
                   int64_t n_samples, int64_t ld, int64_t pad, T *__restrict__ partial,
                   int64_t n_split) {
     const int64_t rb = blockIdx.y;             // receiver * B + band
@@ -151,7 +157,7 @@ k_collect_partial(const T *__restrict__ e_total, const int32_t *__restrict__ rdi
             if (sc == T(0)) continue;          // invisible patch (CTA-uniform)
             int64_t ts = t - shift[rk];
             if (ts < 0) ts += n_samples;       // circular np.roll
-            acc += e_total[((k * n_dirs + rdir[rk]) * n_bands + b) * ld + pad + ts] * sc;
+            acc += e_total[((b * n_alloc + k) * n_dirs + rdir[rk]) * ld + pad + ts] * sc;
         }
         partial[((split * gridDim.y) + rb) * n_samples + t] = acc;
     }
@@ -171,7 +177,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_collect_patchwise(const T *__restrict__ e_total, const int32_t *__restrict__ rdir,
                     const int32_t *__restrict__ shift, const T *__restrict__ scale,
-                    int64_t n_patches, int64_t n_dirs, int64_t n_bands,
+                    int64_t n_patches, int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
                     int64_t n_samples, int64_t ld, int64_t pad, T *__restrict__ out) {
     const int64_t rkb = blockIdx.x;            // (receiver * N + patch) * B + band
     const int64_t b = rkb % n_bands;
@@ -182,7 +188,7 @@ k_collect_patchwise(const T *__restrict__ e_total, const int32_t *__restrict__ r
     int64_t ts = t - shift[rk];
     if (ts < 0) ts += n_samples;
     out[rkb * n_samples + t] =
-        e_total[((k * n_dirs + rdir[rk]) * n_bands + b) * ld + pad + ts] *
+        e_total[((b * n_alloc + k) * n_dirs + rdir[rk]) * ld + pad + ts] *
         scale[rk * n_bands + b];
 }
 
@@ -191,44 +197,46 @@ k_collect_patchwise(const T *__restrict__ e_total, const int32_t *__restrict__ r
 // ---------------------------------------------------------------------------
 template <typename T>
 int init_t(void *e_total, void *e_prev, const void *e0, const int32_t *delay0,
-           int64_t n_patches, int64_t db, int64_t n_samples, int64_t ld, int64_t pad,
-           cudaStream_t st) {
-    const int64_t n_rows = n_patches * db;
+           int64_t n_patches, int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
+           int64_t n_samples, int64_t ld, int64_t pad, cudaStream_t st) {
+    const int64_t n_rows = n_alloc * n_dirs * n_bands;
     SPB_CUDA(cudaMemsetAsync(e_total, 0, sizeof(T) * n_rows * ld, st));
     if (e_prev) SPB_CUDA(cudaMemsetAsync(e_prev, 0, sizeof(T) * n_rows * ld, st));
-    if (n_rows == 0) return 0;
-    k_init_scatter<T><<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(
-        (T *)e_total, (T *)e_prev, (const T *)e0, delay0, n_rows, db, n_samples, ld, pad);
+    const int64_t n_in = n_patches * n_dirs * n_bands;
+    if (n_in == 0) return 0;
+    k_init_scatter<T><<<(unsigned)ceil_div(n_in, 256), 256, 0, st>>>(
+        (T *)e_total, (T *)e_prev, (const T *)e0, delay0, n_patches, n_alloc, n_dirs, n_bands,
+        n_samples, ld, pad);
     return check_launch("k_init_scatter");
 }
 
 template <typename T>
 int gather_t(const void *e_prev, void *g, const int64_t *seg_ptr, const int32_t *src,
-             const void *wgt, const int32_t *dly, int64_t n_patches, int64_t n_classes,
-             int64_t n_bands, int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
-             int64_t pad, cudaStream_t st) {
-    const int64_t n_j = j_hi - j_lo;
-    const int64_t n_work = n_classes * n_j * n_bands;
+             const void *wgt, const int32_t *dly, int64_t n_patches, int64_t n_alloc,
+             int64_t n_classes, int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+             int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, cudaStream_t st) {
+    const int64_t n_j = j_hi - j_lo, n_b = b_hi - b_lo;
+    const int64_t n_work = n_classes * n_j * n_b;
     if (n_work == 0) return 0;
     dim3 grid((unsigned)ceil_div(n_work, kWarpsPerCta), (unsigned)(t_pad / kTimeTile));
     k_gather<T><<<grid, kWarpsPerCta * 32, 0, st>>>(
-        (const T *)e_prev, (T *)g, seg_ptr, src, (const T *)wgt, dly, n_patches,
-        n_classes, n_bands, j_lo, n_j, ld, pad);
+        (const T *)e_prev, (T *)g, seg_ptr, src, (const T *)wgt, dly, n_patches, n_alloc,
+        n_classes, n_dirs, b_lo, n_b, j_lo, n_j, ld, pad);
     return check_launch("k_gather");
 }
 
 template <typename T>
 int mix_t(const void *g, void *e_cur, void *e_total, const int64_t *seg_ptr,
-          const void *coef, int64_t n_patches, int64_t n_classes, int64_t n_dirs,
-          int64_t n_bands, int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
-          int64_t pad, cudaStream_t st) {
-    const int64_t n_j = j_hi - j_lo;
-    if (n_j == 0) return 0;
-    SPB_REQUIRE(n_j * n_bands <= 2147483647LL, "too many (patch, band) rows");
-    dim3 grid((unsigned)(n_j * n_bands), (unsigned)ceil_div(t_pad, 256));
+          const void *coef, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
+          int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+          int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, cudaStream_t st) {
+    const int64_t n_j = j_hi - j_lo, n_b = b_hi - b_lo;
+    if (n_j * n_b == 0) return 0;
+    SPB_REQUIRE(n_j * n_b <= 2147483647LL, "too many (patch, band) rows");
+    dim3 grid((unsigned)(n_j * n_b), (unsigned)ceil_div(t_pad, 256));
     k_mix<T><<<grid, 256, 0, st>>>(
-        (const T *)g, (T *)e_cur, (T *)e_total, seg_ptr, (const T *)coef, n_patches,
-        n_classes, n_dirs, n_bands, j_lo, t_pad, ld, pad);
+        (const T *)g, (T *)e_cur, (T *)e_total, seg_ptr, (const T *)coef, n_patches, n_alloc,
+        n_classes, n_dirs, n_bands, b_lo, j_lo, n_j, t_pad, ld, pad);
     return check_launch("k_mix");
 }
 
@@ -265,82 +273,91 @@ int spb_exchange_layout(int64_t n_samples, int64_t max_delay, int dtype, int64_t
 }
 
 int spb_exchange_init(void *e_total, void *e_prev, const void *e0, const int32_t *delay0,
-                      int64_t n_patches, int64_t db, int64_t n_samples, int64_t ld,
-                      int64_t pad, int dtype, void *stream) {
+                      int64_t n_patches, int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
+                      int64_t n_samples, int64_t ld, int64_t pad, int dtype, void *stream) {
     SPB_REQUIRE(e_total && e0 && delay0, "null pointer");
     SPB_REQUIRE(ld >= pad + n_samples, "ld < pad + n_samples");
+    SPB_REQUIRE(n_alloc >= n_patches, "n_alloc < n_patches");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SPB_F64)
-        return init_t<double>(e_total, e_prev, e0, delay0, n_patches, db, n_samples, ld, pad, st);
+        return init_t<double>(e_total, e_prev, e0, delay0, n_patches, n_alloc, n_dirs, n_bands,
+                              n_samples, ld, pad, st);
     if (dtype == SPB_F32)
-        return init_t<float>(e_total, e_prev, e0, delay0, n_patches, db, n_samples, ld, pad, st);
+        return init_t<float>(e_total, e_prev, e0, delay0, n_patches, n_alloc, n_dirs, n_bands,
+                             n_samples, ld, pad, st);
     return fail(-1, "invalid argument", "dtype");
 }
 
+#define SPB_CHECK_RANGES()                                                                  \
+    SPB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= n_patches, "receiver range");         \
+    SPB_REQUIRE(0 <= b_lo && b_lo <= b_hi && b_hi <= n_bands, "band range");               \
+    SPB_REQUIRE(n_alloc >= n_patches, "n_alloc < n_patches");                              \
+    SPB_REQUIRE(t_pad % kTimeTile == 0 && ld == pad + t_pad, "layout (use spb_exchange_layout)")
+
 int spb_exchange_gather(const void *e_prev, void *g, const int64_t *seg_ptr,
                         const int32_t *src, const void *wgt, const int32_t *dly,
-                        int64_t n_patches, int64_t n_classes, int64_t n_bands,
-                        int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
-                        int64_t pad, int dtype, void *stream) {
+                        int64_t n_patches, int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
+                        int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+                        int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, int dtype,
+                        void *stream) {
     SPB_REQUIRE(e_prev && g && seg_ptr, "null pointer");
-    SPB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= n_patches, "receiver range");
-    SPB_REQUIRE(t_pad % kTimeTile == 0 && ld == pad + t_pad, "layout (use spb_exchange_layout)");
+    SPB_CHECK_RANGES();
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SPB_F64)
-        return gather_t<double>(e_prev, g, seg_ptr, src, wgt, dly, n_patches, n_classes,
-                                n_bands, j_lo, j_hi, t_pad, ld, pad, st);
+        return gather_t<double>(e_prev, g, seg_ptr, src, wgt, dly, n_patches, n_alloc,
+                                n_classes, n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     if (dtype == SPB_F32)
-        return gather_t<float>(e_prev, g, seg_ptr, src, wgt, dly, n_patches, n_classes,
-                               n_bands, j_lo, j_hi, t_pad, ld, pad, st);
+        return gather_t<float>(e_prev, g, seg_ptr, src, wgt, dly, n_patches, n_alloc,
+                               n_classes, n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     return fail(-1, "invalid argument", "dtype");
 }
 
 int spb_exchange_mix(const void *g, void *e_cur, void *e_total, const int64_t *seg_ptr,
-                     const void *coef, int64_t n_patches, int64_t n_classes,
-                     int64_t n_dirs, int64_t n_bands, int64_t j_lo, int64_t j_hi,
-                     int64_t t_pad, int64_t ld, int64_t pad, int dtype, void *stream) {
+                     const void *coef, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
+                     int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi,
+                     int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad,
+                     int dtype, void *stream) {
     SPB_REQUIRE(g && e_cur && e_total && seg_ptr && coef, "null pointer");
-    SPB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= n_patches, "receiver range");
-    SPB_REQUIRE(ld == pad + t_pad, "layout (use spb_exchange_layout)");
+    SPB_CHECK_RANGES();
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SPB_F64)
-        return mix_t<double>(g, e_cur, e_total, seg_ptr, coef, n_patches, n_classes,
-                             n_dirs, n_bands, j_lo, j_hi, t_pad, ld, pad, st);
+        return mix_t<double>(g, e_cur, e_total, seg_ptr, coef, n_patches, n_alloc, n_classes,
+                             n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     if (dtype == SPB_F32)
-        return mix_t<float>(g, e_cur, e_total, seg_ptr, coef, n_patches, n_classes,
-                            n_dirs, n_bands, j_lo, j_hi, t_pad, ld, pad, st);
+        return mix_t<float>(g, e_cur, e_total, seg_ptr, coef, n_patches, n_alloc, n_classes,
+                            n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     return fail(-1, "invalid argument", "dtype");
 }
 
 int spb_energy_exchange(const void *e0, const int32_t *delay0, const int64_t *seg_ptr,
                         const int32_t *src, const void *wgt, const int32_t *dly,
                         const int64_t *ent_ptr, const void *recs, const void *coef,
-                        int64_t n_patches, int64_t n_classes,
-                        int64_t n_dirs, int64_t n_bands, int64_t n_samples,
-                        int64_t t_pad, int64_t pad, int64_t max_order, void *e_total,
-                        void *e_a, void *e_b, void *g, int dtype, void *stream) {
+                        int64_t n_patches, int64_t n_classes, int64_t n_dirs,
+                        int64_t n_bands, int64_t n_samples, int64_t t_pad, int64_t pad,
+                        int64_t max_order, void *e_total, void *e_a, void *e_b, void *g,
+                        int dtype, void *stream) {
     const int64_t ld = pad + t_pad;
-    const int64_t db = n_dirs * n_bands;
-    int rc = spb_exchange_init(e_total, max_order >= 1 ? e_a : nullptr, e0, delay0,
-                               n_patches, db, n_samples, ld, pad, dtype, stream);
+    const int64_t n = n_patches;
+    int rc = spb_exchange_init(e_total, max_order >= 1 ? e_a : nullptr, e0, delay0, n, n,
+                               n_dirs, n_bands, n_samples, ld, pad, dtype, stream);
     if (rc) return rc;
     if (max_order < 1) return 0;
     SPB_REQUIRE(e_a && e_b && g, "null workspace");
     // e_b's pre-roll must be zero as well (e_a was zeroed by init)
     const size_t esz = dtype == SPB_F64 ? 8 : 4;
-    SPB_CUDA(cudaMemsetAsync(e_b, 0, esz * n_patches * db * ld, (cudaStream_t)stream));
+    SPB_CUDA(cudaMemsetAsync(e_b, 0, esz * n * n_dirs * n_bands * ld, (cudaStream_t)stream));
     void *prev = e_a, *cur = e_b;
     for (int64_t k = 0; k < max_order; ++k) {
         if (recs)
-            rc = spb_exchange_gather_tiled(prev, g, ent_ptr, recs, n_patches, n_classes,
-                                           n_bands, 0, n_patches, t_pad, ld, pad, dtype,
+            rc = spb_exchange_gather_tiled(prev, g, ent_ptr, recs, n, n, n_classes, n_dirs,
+                                           n_bands, 0, n_bands, 0, n, t_pad, ld, pad, dtype,
                                            stream);
         else
-            rc = spb_exchange_gather(prev, g, seg_ptr, src, wgt, dly, n_patches, n_classes,
-                                     n_bands, 0, n_patches, t_pad, ld, pad, dtype, stream);
+            rc = spb_exchange_gather(prev, g, seg_ptr, src, wgt, dly, n, n, n_classes, n_dirs,
+                                     n_bands, 0, n_bands, 0, n, t_pad, ld, pad, dtype, stream);
         if (rc) return rc;
-        rc = spb_exchange_mix(g, cur, e_total, seg_ptr, coef, n_patches, n_classes,
-                              n_dirs, n_bands, 0, n_patches, t_pad, ld, pad, dtype, stream);
+        rc = spb_exchange_mix(g, cur, e_total, seg_ptr, coef, n, n, n_classes, n_dirs, n_bands,
+                              0, n_bands, 0, n, t_pad, ld, pad, dtype, stream);
         if (rc) return rc;
         void *tmp = prev; prev = cur; cur = tmp;
     }
@@ -349,9 +366,9 @@ int spb_energy_exchange(const void *e0, const int32_t *delay0, const int64_t *se
 
 int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *shift,
                      const void *scale, int64_t n_receivers, int64_t n_patches,
-                     int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
-                     int64_t pad, void *mono, void *partial, int64_t n_split, int dtype,
-                     void *stream) {
+                     int64_t n_alloc, int64_t n_dirs, int64_t n_bands, int64_t n_samples,
+                     int64_t ld, int64_t pad, void *mono, void *partial, int64_t n_split,
+                     int dtype, void *stream) {
     SPB_REQUIRE(e_total && rdir && shift && scale && mono && partial, "null pointer");
     SPB_REQUIRE(n_split >= 1 && n_split <= 65535, "n_split");
     SPB_REQUIRE(n_receivers * n_bands <= 65535, "n_receivers * n_bands > 65535: batch the receivers");
@@ -362,8 +379,8 @@ int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *sh
     const int64_t n_out = n_receivers * n_bands * n_samples;
     if (dtype == SPB_F64) {
         k_collect_partial<double><<<grid, 256, 0, st>>>(
-            (const double *)e_total, rdir, shift, (const double *)scale, n_patches, n_dirs,
-            n_bands, n_samples, ld, pad, (double *)partial, n_split);
+            (const double *)e_total, rdir, shift, (const double *)scale, n_patches, n_alloc,
+            n_dirs, n_bands, n_samples, ld, pad, (double *)partial, n_split);
         int rc = check_launch("k_collect_partial");
         if (rc) return rc;
         k_collect_reduce<double><<<(unsigned)ceil_div(n_out, 256), 256, 0, st>>>(
@@ -372,8 +389,8 @@ int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *sh
     }
     if (dtype == SPB_F32) {
         k_collect_partial<float><<<grid, 256, 0, st>>>(
-            (const float *)e_total, rdir, shift, (const float *)scale, n_patches, n_dirs,
-            n_bands, n_samples, ld, pad, (float *)partial, n_split);
+            (const float *)e_total, rdir, shift, (const float *)scale, n_patches, n_alloc,
+            n_dirs, n_bands, n_samples, ld, pad, (float *)partial, n_split);
         int rc = check_launch("k_collect_partial");
         if (rc) return rc;
         k_collect_reduce<float><<<(unsigned)ceil_div(n_out, 256), 256, 0, st>>>(
@@ -385,8 +402,8 @@ int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *sh
 
 int spb_collect_patchwise(const void *e_total, const int32_t *rdir, const int32_t *shift,
                           const void *scale, int64_t n_receivers, int64_t n_patches,
-                          int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
-                          int64_t pad, void *out, int dtype, void *stream) {
+                          int64_t n_alloc, int64_t n_dirs, int64_t n_bands, int64_t n_samples,
+                          int64_t ld, int64_t pad, void *out, int dtype, void *stream) {
     SPB_REQUIRE(e_total && rdir && shift && scale && out, "null pointer");
     const int64_t rows = n_receivers * n_patches * n_bands;
     if (rows == 0) return 0;
@@ -395,12 +412,12 @@ int spb_collect_patchwise(const void *e_total, const int32_t *rdir, const int32_
     dim3 grid((unsigned)rows, (unsigned)ceil_div(n_samples, 256));
     if (dtype == SPB_F64)
         k_collect_patchwise<double><<<grid, 256, 0, st>>>(
-            (const double *)e_total, rdir, shift, (const double *)scale, n_patches, n_dirs,
-            n_bands, n_samples, ld, pad, (double *)out);
+            (const double *)e_total, rdir, shift, (const double *)scale, n_patches, n_alloc,
+            n_dirs, n_bands, n_samples, ld, pad, (double *)out);
     else if (dtype == SPB_F32)
         k_collect_patchwise<float><<<grid, 256, 0, st>>>(
-            (const float *)e_total, rdir, shift, (const float *)scale, n_patches, n_dirs,
-            n_bands, n_samples, ld, pad, (float *)out);
+            (const float *)e_total, rdir, shift, (const float *)scale, n_patches, n_alloc,
+            n_dirs, n_bands, n_samples, ld, pad, (float *)out);
     else
         return fail(-1, "invalid argument", "dtype");
     return check_launch("k_collect_patchwise");

@@ -92,8 +92,9 @@ template <typename T>
 __global__ void __launch_bounds__((kWarpsT + 1) * 32, 2)
 k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
              const int64_t *__restrict__ ent_ptr, const TileRecord<T> *__restrict__ recs,
-             int64_t n_patches, int64_t n_blocks, int64_t n_bands, int64_t jb_lo,
-             int64_t n_jb, int64_t n_classes, int64_t t_pad, int64_t ld, int64_t pad) {
+             int64_t n_patches, int64_t n_alloc, int64_t n_blocks, int64_t n_dirs,
+             int64_t b_lo, int64_t jb_lo, int64_t n_jb, int64_t n_classes, int64_t t_pad,
+             int64_t ld, int64_t pad) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Stage<T> *stages = reinterpret_cast<Stage<T> *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(Stage<T>) * kStages);
@@ -102,8 +103,8 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int64_t n_local = n_classes * n_jb;
-    const int64_t b = blockIdx.x / n_local;
-    const int64_t loc = blockIdx.x - b * n_local;
+    const int64_t b = b_lo + blockIdx.x / n_local;
+    const int64_t loc = blockIdx.x % n_local;
     const int64_t c = loc / n_jb;
     const int64_t jb = jb_lo + (loc - c * n_jb);
     const int64_t tile = c * n_blocks + jb;
@@ -123,8 +124,7 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
 
     if (warp == kWarpsT) {
         // ---------------- producer warp ----------------
-        const T *band_base = e_prev + b * ld + pad + t0 - kBucket;
-        const int64_t row_stride = n_bands * ld;
+        const T *band_base = e_prev + b * n_alloc * n_dirs * ld + pad + t0 - kBucket;
         const uint32_t win_bytes = (uint32_t)(sizeof(T) * (n_active * kSliceT + kBucket));
         const uint32_t tx_bytes = win_bytes + (uint32_t)sizeof(TileRecord<T>);
         int stage = 0;
@@ -139,7 +139,7 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
                 if (lane == 0) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], tx_bytes);
-                    bulk_g2s(stages[stage].window, band_base + (int64_t)sk * row_stride - dk,
+                    bulk_g2s(stages[stage].window, band_base + (int64_t)sk * ld - dk,
                              win_bytes, &full[stage]);
                     bulk_g2s(&stages[stage].rec, recs + e + k, sizeof(TileRecord<T>),
                              &full[stage]);
@@ -194,7 +194,7 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
         for (int s = 0; s < kR; ++s) {
             const int64_t j = jb * kR + s;
             if (j < n_patches) {
-                T *out = g + ((c * n_patches + j) * n_bands + b) * ld + pad + t0 +
+                T *out = g + ((b * n_classes + c) * n_patches + j) * ld + pad + t0 +
                          warp * kSliceT + lane;
 #pragma unroll
                 for (int v = 0; v < kChunksT; ++v) out[32 * v] = acc[s][v];
@@ -205,12 +205,13 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
 
 template <typename T>
 int gather_tiled_t(const void *e_prev, void *g, const int64_t *ent_ptr, const void *recs,
-                   int64_t n_patches, int64_t n_classes, int64_t n_bands, int64_t j_lo,
-                   int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, cudaStream_t st) {
+                   int64_t n_patches, int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
+                   int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi, int64_t t_pad,
+                   int64_t ld, int64_t pad, cudaStream_t st) {
     const int64_t n_blocks = ceil_div(n_patches, kR);
     const int64_t jb_lo = j_lo / kR, jb_hi = ceil_div(j_hi, kR);
     const int64_t n_jb = jb_hi - jb_lo;
-    const int64_t n_cta = n_classes * n_jb * n_bands;
+    const int64_t n_cta = n_classes * n_jb * (b_hi - b_lo);
     if (n_cta == 0) return 0;
     SPB_REQUIRE(n_cta <= 2147483647LL, "too many tiles for one launch");
     const size_t smem = sizeof(Stage<T>) * kStages + 2 * kStages * sizeof(uint64_t);
@@ -222,8 +223,8 @@ int gather_tiled_t(const void *e_prev, void *g, const int64_t *ent_ptr, const vo
     }
     dim3 grid((unsigned)n_cta, (unsigned)ceil_div(t_pad, kCtaT));
     k_gather_tma<T><<<grid, (kWarpsT + 1) * 32, smem, st>>>(
-        (const T *)e_prev, (T *)g, ent_ptr, (const TileRecord<T> *)recs, n_patches, n_blocks,
-        n_bands, jb_lo, n_jb, n_classes, t_pad, ld, pad);
+        (const T *)e_prev, (T *)g, ent_ptr, (const TileRecord<T> *)recs, n_patches, n_alloc,
+        n_blocks, n_dirs, b_lo, jb_lo, n_jb, n_classes, t_pad, ld, pad);
     return check_launch("k_gather_tma");
 }
 
@@ -243,21 +244,26 @@ int spb_tile_geometry(int dtype, int64_t *receivers_per_tile, int64_t *delay_buc
 }
 
 int spb_exchange_gather_tiled(const void *e_prev, void *g, const int64_t *ent_ptr,
-                              const void *recs, int64_t n_patches, int64_t n_classes,
-                              int64_t n_bands, int64_t j_lo, int64_t j_hi, int64_t t_pad,
-                              int64_t ld, int64_t pad, int dtype, void *stream) {
+                              const void *recs, int64_t n_patches, int64_t n_alloc,
+                              int64_t n_classes, int64_t n_dirs, int64_t n_bands,
+                              int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi,
+                              int64_t t_pad, int64_t ld, int64_t pad, int dtype,
+                              void *stream) {
     SPB_REQUIRE(e_prev && g && ent_ptr, "null pointer");
     SPB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= n_patches, "receiver range");
-    SPB_REQUIRE(j_lo % kR == 0, "j_lo must be a multiple of the receiver tile (8)");
+    SPB_REQUIRE(0 <= b_lo && b_lo <= b_hi && b_hi <= n_bands, "band range");
+    SPB_REQUIRE(n_alloc >= n_patches, "n_alloc < n_patches");
+    SPB_REQUIRE(j_lo == j_hi || j_lo % kR == 0,
+                "j_lo must be a multiple of the receiver tile (8)");
     SPB_REQUIRE(t_pad % kTileT == 0 && ld == pad + t_pad, "layout (use spb_exchange_layout)");
     SPB_REQUIRE(pad % kBucket == 0 && pad >= 2 * kBucket, "pad (use spb_exchange_layout)");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SPB_F64)
-        return gather_tiled_t<double>(e_prev, g, ent_ptr, recs, n_patches, n_classes, n_bands,
-                                      j_lo, j_hi, t_pad, ld, pad, st);
+        return gather_tiled_t<double>(e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_classes,
+                                      n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     if (dtype == SPB_F32)
-        return gather_tiled_t<float>(e_prev, g, ent_ptr, recs, n_patches, n_classes, n_bands,
-                                     j_lo, j_hi, t_pad, ld, pad, st);
+        return gather_tiled_t<float>(e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_classes,
+                                     n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     return fail(-1, "invalid argument", "dtype");
 }
 

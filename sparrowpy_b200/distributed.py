@@ -3,13 +3,19 @@
 north_star (3): receiver-side patches are sharded across 1/2/4/8 GPUs with an
 all-gather of the per-order patch energy over NVLink.  One process per GPU
 (``torch.distributed``); rank r owns the receiver patches
-``[r*S, min((r+1)*S, N))`` with ``S = ceil(N / world)``.  Every rank holds the full
-previous-order histogram ``E_{k-1}`` (all senders), computes its slice of ``E_k``
-(stage 1 + stage 2 restricted to its receivers) and the slices are exchanged with
-one all-gather per order.  ``E_total`` stays sharded until the end.
+``[r*S, min((r+1)*S, N))``, ``S = ceil(N / world)`` rounded up to the receiver tile.
+Every rank holds the full previous-order histogram ``E_{k-1}`` (all senders),
+computes its slice of ``E_k`` (stage 1 + stage 2 restricted to its receivers) and the
+slices are exchanged with an all-gather per order.  ``E_total`` stays sharded until
+the end.
 
-The histogram buffers are allocated for ``world * S`` patches so that every shard
-has the same number of rows (NCCL all-gather needs equal counts); the padding
+Bands never mix (RadiosityFast.py:1137-1143 acts per band), and the histogram layout
+is band-major, so with more than one band the schedule is pipelined per band: band
+b's slices are all-gathered on a side stream while the kernels of the other bands
+run; order k+1 of band b only waits for band b's gather of order k.
+
+The buffers are allocated for ``n_alloc = world * S`` patches per band so that every
+shard has the same number of rows (NCCL all-gather needs equal counts); the padding
 patches own no pairs and stay zero.
 """
 import os
@@ -19,7 +25,6 @@ import torch.distributed as dist
 
 from . import _lib
 from .exchange import EnergyHistogram
-
 
 SHARD_ALIGN = 8
 
@@ -36,9 +41,9 @@ def shard_range(n_patches, rank, world):
 class ShardedExchange:
     """Per-order orchestration: local gather+mix, then all-gather of ``E_k``.
 
-    ``compute`` is the per-order local step; the default launches the CUDA kernels
-    through the C ABI.  Tests substitute a CPU function to exercise the collective
-    choreography under gloo.
+    ``compute(prev, cur, total, b_lo, b_hi)`` is the local step for a band range; the
+    default launches the CUDA kernels through the C ABI.  Tests substitute a CPU
+    function to exercise the collective choreography under gloo.
     """
 
     def __init__(self, tables, n_samples, device, group=None, compute=None,
@@ -50,80 +55,129 @@ class ShardedExchange:
         self.n_samples = n_samples
         self.j_lo, self.j_hi, self.shard = shard_range(tables.n_patches, self.rank,
                                                        self.world)
-        self.n_pad = self.shard * self.world
+        self.n_alloc = self.shard * self.world if self.world > 1 else tables.n_patches
         if layout is None:
             layout = _lib.exchange_layout(n_samples, tables.max_delay, tables.dtype)
         self.t_pad, self.pad = layout
         self.ld = self.t_pad + self.pad
         tdt = _lib.torch_dtype(tables.dtype)
-        self.db = tables.n_dirs * tables.n_bands
-        rows = self.n_pad * self.db
+        t = tables
+        rows = t.n_bands * self.n_alloc * t.n_dirs
         self.e_a = torch.zeros((rows, self.ld), dtype=tdt, device=device)
         self.e_b = torch.zeros((rows, self.ld), dtype=tdt, device=device)
         self.e_total = torch.zeros((rows, self.ld), dtype=tdt, device=device)
-        g_rows = tables.n_classes * tables.n_patches * tables.n_bands
+        g_rows = t.n_bands * t.n_classes * t.n_patches
         self.g = torch.empty((max(g_rows, 1), self.ld), dtype=tdt, device=device)
         self.compute = compute or self._cuda_order
+        self.cuda = torch.device(device).type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=device) if (
+            self.cuda and self.world > 1) else None
 
     # -- local kernels -------------------------------------------------------
-    def _cuda_order(self, prev, cur, total):
+    def _cuda_order(self, prev, cur, total, b_lo, b_hi):
         t = self.t
         code = _lib.I32(t.dtype)
         st = _lib.stream_ptr()
         if t.recs is not None and os.environ.get("SPB_GATHER", "tma") != "csr":
             _lib.call("spb_exchange_gather_tiled", prev, self.g, t.ent_ptr, t.recs,
-                      t.n_patches, t.n_classes, t.n_bands, self.j_lo, self.j_hi, self.t_pad,
-                      self.ld, self.pad, code, st)
+                      t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
+                      b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad, code, st)
         else:
             _lib.call("spb_exchange_gather", prev, self.g, t.seg_ptr, t.src, t.wgt, t.dly,
-                      t.n_patches, t.n_classes, t.n_bands, self.j_lo, self.j_hi,
-                      self.t_pad, self.ld, self.pad, code, st)
+                      t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
+                      b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad, code, st)
         _lib.call("spb_exchange_mix", self.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
-                  t.n_classes, t.n_dirs, t.n_bands, self.j_lo, self.j_hi, self.t_pad,
-                  self.ld, self.pad, code, st)
+                  self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, self.j_lo,
+                  self.j_hi, self.t_pad, self.ld, self.pad, code, st)
 
-    def _shard_rows(self, buf, rank=None):
+    # -- row bookkeeping -----------------------------------------------------
+    def band_rows(self, buf, b):
+        """All rows of band ``b`` (every patch)."""
+        n = self.n_alloc * self.t.n_dirs
+        return buf[b * n:(b + 1) * n]
+
+    def shard_rows(self, buf, b, rank=None):
+        """Rows of band ``b`` owned by ``rank``."""
         rank = self.rank if rank is None else rank
-        r0 = rank * self.shard * self.db
-        return buf[r0:r0 + self.shard * self.db]
+        d = self.t.n_dirs
+        r0 = (b * self.n_alloc + rank * self.shard) * d
+        return buf[r0:r0 + self.shard * d]
 
-    def _all_gather(self, buf):
-        if self.world > 1:
-            dist.all_gather_into_tensor(buf, self._shard_rows(buf), group=self.group)
+    def _all_gather_band(self, buf, b):
+        dist.all_gather_into_tensor(self.band_rows(buf, b), self.shard_rows(buf, b),
+                                    group=self.group)
 
     # -- driver --------------------------------------------------------------
     def init(self, e0, delay0):
-        """Initial energy (order 0) into e_total and e_a on every rank (replicated:
-        N*D*B scatters)."""
+        """Initial energy (order 0): replicated into e_a (every rank needs all
+        senders), own shard only into e_total."""
         t = self.t
-        self.e_total.zero_()
-        self.e_a.zero_()
         self.e_b.zero_()
-        if e0.is_cuda:
+        if self.cuda:
             tdt = _lib.torch_dtype(t.dtype)
-            n_rows = t.n_patches * self.db
-            _lib.call("spb_exchange_init", self.e_total[:n_rows], self.e_a[:n_rows],
-                      e0.to(tdt).contiguous(), delay0.to(torch.int32).contiguous(),
-                      t.n_patches, self.db, self.n_samples, self.ld, self.pad,
+            _lib.call("spb_exchange_init", self.e_total, self.e_a, e0.to(tdt).contiguous(),
+                      delay0.to(torch.int32).contiguous(), t.n_patches, self.n_alloc,
+                      t.n_dirs, t.n_bands, self.n_samples, self.ld, self.pad,
                       _lib.I32(t.dtype), _lib.stream_ptr())
         else:  # CPU path of the gloo tests
-            rows = torch.arange(t.n_patches * self.db)
-            d = delay0.long().repeat_interleave(self.db)
-            ok = d < self.n_samples
-            vals = e0.reshape(-1).to(self.e_total.dtype)
-            self.e_total[rows[ok], self.pad + d[ok]] += vals[ok]
-            self.e_a[rows[ok], self.pad + d[ok]] += vals[ok]
-        # e_total keeps only this rank's shard (the final all-gather assembles it)
-        keep = self._shard_rows(self.e_total).clone()
-        self.e_total.zero_()
-        self._shard_rows(self.e_total).copy_(keep)
+            self.e_total.zero_()
+            self.e_a.zero_()
+            n, d, nb = e0.shape
+            for b in range(nb):
+                for i in range(n):
+                    dl = int(delay0[i])
+                    if dl < self.n_samples:
+                        r0 = (b * self.n_alloc + i) * d
+                        self.e_total[r0:r0 + d, self.pad + dl] += e0[i, :, b].to(
+                            self.e_total.dtype)
+            self.e_a.copy_(self.e_total)
+        if self.world > 1:
+            keep = [self.shard_rows(self.e_total, b).clone() for b in range(t.n_bands)]
+            self.e_total.zero_()
+            for b in range(t.n_bands):
+                self.shard_rows(self.e_total, b).copy_(keep[b])
 
     def run(self, max_order):
+        t = self.t
+        nb = t.n_bands
         prev, cur = self.e_a, self.e_b
-        for _ in range(max_order):
-            self.compute(prev, cur, self.e_total)
-            self._all_gather(cur)
-            prev, cur = cur, prev
-        self._all_gather(self.e_total)
-        return EnergyHistogram(self.e_total[:self.t.n_patches * self.db], self.t.n_patches,
-                               self.t.n_dirs, self.t.n_bands, self.n_samples, self.pad)
+        if self.world == 1:
+            for _ in range(max_order):
+                self.compute(prev, cur, self.e_total, 0, nb)
+                prev, cur = cur, prev
+        elif not self.cuda:
+            for _ in range(max_order):
+                self.compute(prev, cur, self.e_total, 0, nb)
+                for b in range(nb):
+                    self._all_gather_band(cur, b)
+                prev, cur = cur, prev
+            for b in range(nb):
+                self._all_gather_band(self.e_total, b)
+        else:
+            comp = torch.cuda.current_stream()
+            comm = self.comm_stream
+            comm.wait_stream(comp)
+            ready = [None] * nb           # band b of `prev` is complete on every rank
+            for _ in range(max_order):
+                nxt = []
+                for b in range(nb):
+                    if ready[b] is not None:
+                        comp.wait_event(ready[b])
+                    self.compute(prev, cur, self.e_total, b, b + 1)
+                    done = torch.cuda.Event()
+                    done.record(comp)
+                    comm.wait_event(done)
+                    with torch.cuda.stream(comm):
+                        self._all_gather_band(cur, b)
+                        ev = torch.cuda.Event()
+                        ev.record(comm)
+                    nxt.append(ev)
+                ready = nxt
+                prev, cur = cur, prev
+            for ev in ready:
+                if ev is not None:
+                    comp.wait_event(ev)
+            for b in range(nb):
+                self._all_gather_band(self.e_total, b)
+        return EnergyHistogram(self.e_total, t.n_patches, t.n_dirs, t.n_bands,
+                               self.n_samples, self.pad, n_alloc=self.n_alloc)

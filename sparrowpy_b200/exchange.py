@@ -153,21 +153,24 @@ def build_tile_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_d
 
 
 class EnergyHistogram:
-    """(patch, direction, band, time) histogram in the padded-row device layout."""
+    """(patch, direction, band, time) histogram in the padded-row device layout:
+    ``data[(band * n_alloc + patch) * D + dir, PAD + t]``."""
 
-    def __init__(self, data, n_patches, n_dirs, n_bands, n_samples, pad):
-        self.data = data                    # (N*D*B, LD)
+    def __init__(self, data, n_patches, n_dirs, n_bands, n_samples, pad, n_alloc=None):
+        self.data = data                    # (B * n_alloc * D, LD)
         self.n_patches, self.n_dirs = n_patches, n_dirs
         self.n_bands, self.n_samples, self.pad = n_bands, n_samples, pad
+        self.n_alloc = n_patches if n_alloc is None else n_alloc
 
     @property
     def ld(self):
         return self.data.shape[1]
 
     def dense(self):
-        """(N, D, B, T) view without padding (still on the device)."""
-        v = self.data[:, self.pad:self.pad + self.n_samples]
-        return v.reshape(self.n_patches, self.n_dirs, self.n_bands, self.n_samples)
+        """(N, D, B, T) view in the reference's axis order (device, strided)."""
+        v = self.data.view(self.n_bands, self.n_alloc, self.n_dirs, self.ld)
+        v = v[:, :self.n_patches, :, self.pad:self.pad + self.n_samples]
+        return v.permute(1, 2, 0, 3)
 
 
 class ExchangeWorkspace:
@@ -179,13 +182,13 @@ class ExchangeWorkspace:
         self.ld = self.t_pad + self.pad
         self.n_samples = n_samples
         tdt = _lib.torch_dtype(t.dtype)
-        rows = t.n_patches * t.n_dirs * t.n_bands
+        rows = t.n_bands * t.n_patches * t.n_dirs
         self.e_total = torch.empty((rows, self.ld), dtype=tdt, device=device)
         if need_orders:
             self.e_a = torch.empty((rows, self.ld), dtype=tdt, device=device)
             self.e_b = torch.empty((rows, self.ld), dtype=tdt, device=device)
             # rows of empty segments are never written nor read
-            self.g = torch.empty((t.n_classes * t.n_patches * t.n_bands, self.ld),
+            self.g = torch.empty((t.n_bands * t.n_classes * t.n_patches, self.ld),
                                  dtype=tdt, device=device)
         else:
             self.e_a = self.e_b = self.g = None
@@ -233,7 +236,8 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
                               device=hist.data.device)
         _lib.call("spb_collect_mono", hist.data, rdir[r0:r1].contiguous(),
                   shift[r0:r1].contiguous(), scale[r0:r1].to(tdt).contiguous(), r1 - r0,
-                  hist.n_patches, hist.n_dirs, hist.n_bands, hist.n_samples, hist.ld,
+                  hist.n_patches, hist.n_alloc, hist.n_dirs, hist.n_bands, hist.n_samples,
+                  hist.ld,
                   hist.pad, out[r0:r1], partial, n_split, _lib.I32(code),
                   _lib.stream_ptr())
     return out
@@ -248,8 +252,9 @@ def collect_patchwise(hist, rdir, shift, scale):
     out = torch.empty((n_rcv, hist.n_patches, hist.n_bands, hist.n_samples), dtype=tdt,
                       device=hist.data.device)
     _lib.call("spb_collect_patchwise", hist.data, rdir.contiguous(), shift.contiguous(),
-              scale.to(tdt).contiguous(), n_rcv, hist.n_patches, hist.n_dirs, hist.n_bands,
-              hist.n_samples, hist.ld, hist.pad, out, _lib.I32(code), _lib.stream_ptr())
+              scale.to(tdt).contiguous(), n_rcv, hist.n_patches, hist.n_alloc, hist.n_dirs,
+              hist.n_bands, hist.n_samples, hist.ld, hist.pad, out, _lib.I32(code),
+              _lib.stream_ptr())
     return out
 
 

@@ -388,9 +388,10 @@ class DirectionalRadiosityFast:
             n, d, b, t = etc.shape
             code = _lib.dtype_code(self._dtype)
             t_pad, pad = _lib.exchange_layout(t, 0, code)
-            data = torch.zeros((n * d * b, t_pad + pad), dtype=_lib.torch_dtype(code),
+            data = torch.zeros((b * n * d, t_pad + pad), dtype=_lib.torch_dtype(code),
                                device=self._device)
-            data[:, pad:pad + t] = torch.from_numpy(etc.reshape(n * d * b, t)).to(
+            band_major = np.ascontiguousarray(etc.transpose(2, 0, 1, 3))   # (B, N, D, T)
+            data[:, pad:pad + t] = torch.from_numpy(band_major.reshape(b * n * d, t)).to(
                 self._device)
             self._hist = exchange.EnergyHistogram(data, n, d, b, t, pad)
         return self._hist

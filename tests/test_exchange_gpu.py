@@ -160,16 +160,16 @@ def test_tiled_and_csr_gather_agree_on_ragged_lists():
                                         t_len, "f64")
     t_pad, pad = _lib.exchange_layout(t_len, tables.max_delay, tables.dtype)
     ld = t_pad + pad
-    prev = torch.zeros((n * d * b, ld), dtype=torch.float64, device=dev)
-    prev[:, pad:pad + t_len] = torch.rand((n * d * b, t_len), generator=gen,
+    prev = torch.zeros((b * n * d, ld), dtype=torch.float64, device=dev)
+    prev[:, pad:pad + t_len] = torch.rand((b * n * d, t_len), generator=gen,
                                           dtype=torch.float64).to(dev)
-    g1 = torch.zeros((c * n * b, ld), dtype=torch.float64, device=dev)
+    g1 = torch.zeros((b * c * n, ld), dtype=torch.float64, device=dev)
     g2 = torch.zeros_like(g1)
     st, code = _lib.stream_ptr(), _lib.I32(tables.dtype)
     _lib.call("spb_exchange_gather", prev, g1, tables.seg_ptr, tables.src, tables.wgt,
-              tables.dly, n, c, b, 0, n, t_pad, ld, pad, code, st)
-    _lib.call("spb_exchange_gather_tiled", prev, g2, tables.ent_ptr, tables.recs, n, c, b,
-              0, n, t_pad, ld, pad, code, st)
+              tables.dly, n, n, c, d, b, 0, b, 0, n, t_pad, ld, pad, code, st)
+    _lib.call("spb_exchange_gather_tiled", prev, g2, tables.ent_ptr, tables.recs, n, n, c,
+              d, b, 0, b, 0, n, t_pad, ld, pad, code, st)
     torch.cuda.synchronize()
     a, bb = g1[:, pad:pad + t_len], g2[:, pad:pad + t_len]
     assert torch.allclose(a, bb, rtol=1e-12, atol=1e-14)
@@ -180,7 +180,49 @@ def test_tiled_and_csr_gather_agree_on_ragged_lists():
     sel = (cls == cc) & (receiver == jj) & (delay < t_len)
     ref = torch.zeros(t_len, dtype=torch.float64, device=dev)
     for q in torch.nonzero(sel).reshape(-1).tolist():
-        row = (int(sender[q]) * d + int(out_dir[q])) * b + 1
+        row = 1 * n * d + int(sender[q]) * d + int(out_dir[q])      # band 1
         dl = int(delay[q])
         ref[dl:] += ff[q] * prev[row, pad:pad + t_len - dl]
-    assert torch.allclose(g2[(seg * b) + 1, pad:pad + t_len], ref, rtol=1e-12, atol=1e-14)
+    assert torch.allclose(g2[1 * c * n + seg, pad:pad + t_len], ref, rtol=1e-12, atol=1e-14)
+
+
+def test_sharded_driver_matches_one_call_api(oracle):
+    """distributed.ShardedExchange (world = 1, per-order C-ABI calls) equals
+    spb_energy_exchange (one call), and a 2-shard split run by hand equals both."""
+    from sparrowpy_b200 import _lib, distributed, exchange
+    g = load_golden("scene_directional")
+    out = oracle_run(oracle, g)
+    dev = torch.device("cuda:0")
+    n_samples = out["etc"].shape[-1]
+    tables = device_tables(g, out, "f64", n_samples)
+    e0 = torch.from_numpy(out["energy_init_source"]).to(dev)
+    c, dt = float(g["speed_of_sound"]), float(g["dt"])
+    delay0 = torch.from_numpy(
+        (out["distance_patches_to_source"] / c / dt).astype(np.int32)).to(dev)
+    ref = exchange.energy_exchange(tables, e0, delay0, n_samples, 4).dense().clone()
+    sx = distributed.ShardedExchange(tables, n_samples, dev)
+    sx.init(e0, delay0)
+    got = sx.run(4).dense()
+    assert torch.equal(got, ref)
+    # emulate two ranks on one GPU: each computes its receiver range, rows are merged
+    n = tables.n_patches
+    lo0, hi0, size = distributed.shard_range(n, 0, 2)
+    lo1, hi1, _ = distributed.shard_range(n, 1, 2)
+    assert (lo0, hi1) == (0, n) and hi0 == lo1
+    sx.init(e0, delay0)
+    prev, cur = sx.e_a, sx.e_b
+    code, st = _lib.I32(tables.dtype), _lib.stream_ptr()
+    t = tables
+    for _ in range(4):
+        for lo, hi in ((lo0, hi0), (lo1, hi1)):
+            for b in range(t.n_bands):           # one band at a time, like the pipeline
+                _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
+                          t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b, b + 1,
+                          lo, hi, sx.t_pad, sx.ld, sx.pad, code, st)
+                _lib.call("spb_exchange_mix", sx.g, cur, sx.e_total, t.seg_ptr, t.coef,
+                          t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b, b + 1,
+                          lo, hi, sx.t_pad, sx.ld, sx.pad, code, st)
+        prev, cur = cur, prev
+    got2 = exchange.EnergyHistogram(sx.e_total, n, t.n_dirs, t.n_bands, n_samples, sx.pad,
+                                    n_alloc=sx.n_alloc).dense()
+    assert torch.equal(got2, ref)

@@ -261,9 +261,7 @@ def main():
                       sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32, sp)
         ev1.record(cst)
         gather_events.append((ev0, ev1))
-        _lib.call("spb_exchange_mix", sx.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
-                  sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, sx.j_lo, sx.j_hi,
-                  sx.t_pad, sx.ld, sx.pad, c32, sp)
+        sx._mix(cur, total, b_lo, b_hi)
 
     sx.compute = timed_order
 
@@ -281,7 +279,7 @@ def main():
     barrier()
     gather_events.clear()
     # gather+mix per (order, band launch) + init (memsets + scatter)
-    band_launches = n_band if world > 1 else 1
+    band_launches = n_band if (world > 1 and sx.comm == "nccl") else 1
     launches_per_step = orders * band_launches * 2 + 4
     with ClockSampler(local_rank) as clocks:
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -385,7 +383,8 @@ def main():
                        "l2": "inputs larger than L2" if
                        rad.n_patches * n_dir * n_band * sx.ld * esize > 126e6 * 2
                        else "working set fits L2 (small config, no flush)",
-                       "parallelism": f"receiver shards x{world}" if world > 1 else "1 GPU"},
+                       "parallelism": (f"receiver shards x{world}, exchange: {sx.comm}"
+                                       if world > 1 else "1 GPU")},
             "clocks": clocks.summary(), "roofline": roofline,
         }
         if e2e:

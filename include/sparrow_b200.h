@@ -118,6 +118,22 @@ int spb_exchange_mix(const void *g, void *e_cur, void *e_total,
                      int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi,
                      int64_t t_pad, int64_t ld, int64_t pad, int dtype, void *stream);
 
+/* Stage 2 fused with the per-order exchange of the receiver-sharded run: instead of
+ * writing E_k into the local buffer and all-gathering it afterwards, the kernel
+ * stores every E_k element of this rank's receivers straight into all ranks' copies
+ * of the buffer -- with one NVSwitch multicast store (multimem.st) when
+ * cur_multicast != 0, else with NVLink P2P stores to the n_peers buffers in
+ * cur_ptrs_h (host array of device addresses, own rank included).  The buffers must
+ * be symmetric allocations of identical size (e.g. torch symmetric memory); the
+ * caller separates orders with a cross-rank barrier.  e_total stays local. */
+int spb_exchange_mix_fused(const void *g, const uint64_t *cur_ptrs_h, int n_peers,
+                           void *cur_multicast, void *e_total, const int64_t *seg_ptr,
+                           const void *coef, int64_t n_patches, int64_t n_alloc,
+                           int64_t n_classes, int64_t n_dirs, int64_t n_bands,
+                           int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi,
+                           int64_t t_pad, int64_t ld, int64_t pad, int dtype,
+                           void *stream);
+
 /* `_energy_exchange` (RadiosityFast.py:1073-1145) on one GPU: init + max_order
  * x (gather, mix).  e_a, e_b: ping-pong [B*N*D, LD]; g: [B*C*N, LD].  With recs != 0
  * stage 1 is the tiled TMA kernel, otherwise the CSR kernel.

@@ -96,10 +96,31 @@ k_gather(const T *__restrict__ e_prev, T *__restrict__ g,
 // one CTA per (patch, band, time slab); threads along time
 // ---------------------------------------------------------------------------
 constexpr int kMixDirs = 8;
+constexpr int kMaxPeers = 8;
+
+// Where stage 2 stores E_k: the local buffer (one GPU), every peer's copy of the
+// buffer through NVLink P2P stores, or one NVSwitch multicast store (multimem.st)
+// that the switch replicates into all ranks' copies.  With the peer modes the
+// per-order all-gather of the sharded exchange disappears into this kernel.
+enum : int { kStoreLocal = 0, kStorePeers = 1, kStoreMulticast = 2 };
 
 template <typename T>
+struct StoreTargets {
+    T *ptr[kMaxPeers];      // kStoreLocal: ptr[0]; kStorePeers: all ranks' buffers
+    T *mc;                  // kStoreMulticast: multicast address of the buffer
+    int n;
+};
+
+__device__ __forceinline__ void multimem_store(double *addr, double v) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_store(float *addr, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
-k_mix(const T *__restrict__ g, T *__restrict__ e_cur, T *__restrict__ e_total,
+k_mix(const T *__restrict__ g, StoreTargets<T> cur, T *__restrict__ e_total,
       const int64_t *__restrict__ seg_ptr, const T *__restrict__ coef,
       int64_t n_patches, int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
       int64_t n_bands, int64_t b_lo, int64_t j_lo, int64_t n_j, int64_t t_pad, int64_t ld,
@@ -126,7 +147,13 @@ k_mix(const T *__restrict__ g, T *__restrict__ e_cur, T *__restrict__ e_total,
         for (int dd = 0; dd < kMixDirs; ++dd) {
             if (d0 + dd < n_dirs) {
                 const int64_t o = ((b * n_alloc + j) * n_dirs + d0 + dd) * ld + pad + t;
-                e_cur[o] = acc[dd];
+                if (MODE == kStoreLocal) {
+                    cur.ptr[0][o] = acc[dd];
+                } else if (MODE == kStorePeers) {
+                    for (int p = 0; p < cur.n; ++p) cur.ptr[p][o] = acc[dd];
+                } else {
+                    multimem_store(cur.mc + o, acc[dd]);
+                }
                 e_total[o] += acc[dd];
             }
         }
@@ -226,18 +253,43 @@ int gather_t(const void *e_prev, void *g, const int64_t *seg_ptr, const int32_t 
 }
 
 template <typename T>
-int mix_t(const void *g, void *e_cur, void *e_total, const int64_t *seg_ptr,
-          const void *coef, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
-          int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
-          int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, cudaStream_t st) {
+int mix_t(const void *g, const StoreTargets<T> &cur, int mode, void *e_total,
+          const int64_t *seg_ptr, const void *coef, int64_t n_patches, int64_t n_alloc,
+          int64_t n_classes, int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi,
+          int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad,
+          cudaStream_t st) {
     const int64_t n_j = j_hi - j_lo, n_b = b_hi - b_lo;
     if (n_j * n_b == 0) return 0;
     SPB_REQUIRE(n_j * n_b <= 2147483647LL, "too many (patch, band) rows");
     dim3 grid((unsigned)(n_j * n_b), (unsigned)ceil_div(t_pad, 256));
-    k_mix<T><<<grid, 256, 0, st>>>(
-        (const T *)g, (T *)e_cur, (T *)e_total, seg_ptr, (const T *)coef, n_patches, n_alloc,
-        n_classes, n_dirs, n_bands, b_lo, j_lo, n_j, t_pad, ld, pad);
+#define SPB_MIX_LAUNCH(MODE)                                                                \
+    k_mix<T, MODE><<<grid, 256, 0, st>>>((const T *)g, cur, (T *)e_total, seg_ptr,          \
+                                         (const T *)coef, n_patches, n_alloc, n_classes,    \
+                                         n_dirs, n_bands, b_lo, j_lo, n_j, t_pad, ld, pad)
+    if (mode == kStoreLocal) SPB_MIX_LAUNCH(kStoreLocal);
+    else if (mode == kStorePeers) SPB_MIX_LAUNCH(kStorePeers);
+    else SPB_MIX_LAUNCH(kStoreMulticast);
+#undef SPB_MIX_LAUNCH
     return check_launch("k_mix");
+}
+
+template <typename T>
+int mix_dispatch(const void *g, void *e_cur, const uint64_t *peer_ptrs_h, int n_peers,
+                 void *cur_mc, int mode, void *e_total, const int64_t *seg_ptr,
+                 const void *coef, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
+                 int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+                 int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, cudaStream_t st) {
+    StoreTargets<T> cur;
+    for (int p = 0; p < kMaxPeers; ++p) cur.ptr[p] = nullptr;
+    cur.mc = (T *)cur_mc;
+    cur.n = 1;
+    cur.ptr[0] = (T *)e_cur;
+    if (mode == kStorePeers) {
+        cur.n = n_peers;
+        for (int p = 0; p < n_peers; ++p) cur.ptr[p] = (T *)(uintptr_t)peer_ptrs_h[p];
+    }
+    return mix_t<T>(g, cur, mode, e_total, seg_ptr, coef, n_patches, n_alloc, n_classes,
+                    n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
 }
 
 }  // namespace spb
@@ -321,11 +373,36 @@ int spb_exchange_mix(const void *g, void *e_cur, void *e_total, const int64_t *s
     SPB_CHECK_RANGES();
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SPB_F64)
-        return mix_t<double>(g, e_cur, e_total, seg_ptr, coef, n_patches, n_alloc, n_classes,
-                             n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
+        return mix_dispatch<double>(g, e_cur, nullptr, 1, nullptr, kStoreLocal, e_total,
+                                    seg_ptr, coef, n_patches, n_alloc, n_classes, n_dirs,
+                                    n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     if (dtype == SPB_F32)
-        return mix_t<float>(g, e_cur, e_total, seg_ptr, coef, n_patches, n_alloc, n_classes,
-                            n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
+        return mix_dispatch<float>(g, e_cur, nullptr, 1, nullptr, kStoreLocal, e_total,
+                                   seg_ptr, coef, n_patches, n_alloc, n_classes, n_dirs,
+                                   n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
+    return fail(-1, "invalid argument", "dtype");
+}
+
+int spb_exchange_mix_fused(const void *g, const uint64_t *cur_ptrs_h, int n_peers,
+                           void *cur_multicast, void *e_total, const int64_t *seg_ptr,
+                           const void *coef, int64_t n_patches, int64_t n_alloc,
+                           int64_t n_classes, int64_t n_dirs, int64_t n_bands, int64_t b_lo,
+                           int64_t b_hi, int64_t j_lo, int64_t j_hi, int64_t t_pad,
+                           int64_t ld, int64_t pad, int dtype, void *stream) {
+    SPB_REQUIRE(g && e_total && seg_ptr && coef, "null pointer");
+    SPB_REQUIRE(cur_multicast || (cur_ptrs_h && n_peers >= 1 && n_peers <= kMaxPeers),
+                "need a multicast address or 1..8 peer pointers");
+    SPB_CHECK_RANGES();
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mode = cur_multicast ? kStoreMulticast : kStorePeers;
+    if (dtype == SPB_F64)
+        return mix_dispatch<double>(g, nullptr, cur_ptrs_h, n_peers, cur_multicast, mode,
+                                    e_total, seg_ptr, coef, n_patches, n_alloc, n_classes,
+                                    n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
+    if (dtype == SPB_F32)
+        return mix_dispatch<float>(g, nullptr, cur_ptrs_h, n_peers, cur_multicast, mode,
+                                   e_total, seg_ptr, coef, n_patches, n_alloc, n_classes,
+                                   n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     return fail(-1, "invalid argument", "dtype");
 }
 

@@ -17,6 +17,17 @@ run; order k+1 of band b only waits for band b's gather of order k.
 The buffers are allocated for ``n_alloc = world * S`` patches per band so that every
 shard has the same number of rows (NCCL all-gather needs equal counts); the padding
 patches own no pairs and stay zero.
+
+Communication modes (``SPB_COMM``):
+
+``multicast`` (default when the symmetric allocation has a multicast address) and
+``p2p``: the ping-pong buffers are torch symmetric-memory allocations mapped into
+every rank; stage 2 (``spb_exchange_mix_fused``) stores each ``E_k`` element of the
+rank's receivers directly into all ranks' buffers -- one NVSwitch multicast store
+(``multimem.st``) or one NVLink P2P store per peer -- so the all-gather is fused into
+the compute kernel and only a cross-rank barrier separates the orders of a band.
+``nccl``: local stores + ``all_gather_into_tensor`` on a side stream, pipelined
+per band.
 """
 import os
 
@@ -63,15 +74,43 @@ class ShardedExchange:
         tdt = _lib.torch_dtype(tables.dtype)
         t = tables
         rows = t.n_bands * self.n_alloc * t.n_dirs
-        self.e_a = torch.zeros((rows, self.ld), dtype=tdt, device=device)
-        self.e_b = torch.zeros((rows, self.ld), dtype=tdt, device=device)
+        self.cuda = torch.device(device).type == "cuda"
+        self.comm = "local"
+        self.handles = None
+        if self.world > 1:
+            # P2P stores cost (world-1) x the shard in NVLink egress, a multicast store
+            # 1 x (the switch replicates) but also routes the local copy through the
+            # switch: P2P wins for 2 ranks, multicast beyond
+            default = "p2p" if self.world <= 2 else "multicast"
+            self.comm = os.environ.get("SPB_COMM", default) if self.cuda else "gloo"
+        if self.comm in ("multicast", "p2p"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                self.e_a = symm_mem.empty((rows, self.ld), dtype=tdt, device=device)
+                self.e_b = symm_mem.empty((rows, self.ld), dtype=tdt, device=device)
+                self.handles = {self.e_a.data_ptr(): symm_mem.rendezvous(self.e_a, grp),
+                                self.e_b.data_ptr(): symm_mem.rendezvous(self.e_b, grp)}
+                if self.comm == "multicast" and not all(
+                        h.multicast_ptr for h in self.handles.values()):
+                    self.comm = "p2p"
+                self.e_a.zero_()
+                self.e_b.zero_()
+            except Exception as exc:  # noqa: BLE001
+                if os.environ.get("SPB_COMM"):
+                    raise
+                print(f"[sparrowpy_b200] symmetric memory unavailable ({exc}); "
+                      "using NCCL all-gather", flush=True)
+                self.comm, self.handles = "nccl", None
+        if self.handles is None:
+            self.e_a = torch.zeros((rows, self.ld), dtype=tdt, device=device)
+            self.e_b = torch.zeros((rows, self.ld), dtype=tdt, device=device)
         self.e_total = torch.zeros((rows, self.ld), dtype=tdt, device=device)
         g_rows = t.n_bands * t.n_classes * t.n_patches
         self.g = torch.empty((max(g_rows, 1), self.ld), dtype=tdt, device=device)
         self.compute = compute or self._cuda_order
-        self.cuda = torch.device(device).type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=device) if (
-            self.cuda and self.world > 1) else None
+            self.cuda and self.comm == "nccl") else None
 
     # -- local kernels -------------------------------------------------------
     def _cuda_order(self, prev, cur, total, b_lo, b_hi):
@@ -86,9 +125,29 @@ class ShardedExchange:
             _lib.call("spb_exchange_gather", prev, self.g, t.seg_ptr, t.src, t.wgt, t.dly,
                       t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
                       b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad, code, st)
-        _lib.call("spb_exchange_mix", self.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
-                  self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, self.j_lo,
-                  self.j_hi, self.t_pad, self.ld, self.pad, code, st)
+        self._mix(cur, total, b_lo, b_hi)
+
+    def _mix(self, cur, total, b_lo, b_hi):
+        """Stage 2; with symmetric buffers it also delivers E_k to every rank."""
+        import ctypes
+        t = self.t
+        code = _lib.I32(t.dtype)
+        st = _lib.stream_ptr()
+        if self.handles is None:
+            _lib.call("spb_exchange_mix", self.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
+                      self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, self.j_lo,
+                      self.j_hi, self.t_pad, self.ld, self.pad, code, st)
+            return
+        hdl = self.handles[cur.data_ptr()]
+        ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        mc = ctypes.c_void_p(int(hdl.multicast_ptr) if self.comm == "multicast" else 0)
+        _lib.call("spb_exchange_mix_fused", self.g, ptrs, _lib.I32(self.world), mc, total,
+                  t.seg_ptr, t.coef, t.n_patches, self.n_alloc, t.n_classes, t.n_dirs,
+                  t.n_bands, b_lo, b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad,
+                  code, st)
+
+    def _barrier(self):
+        next(iter(self.handles.values())).barrier(0)
 
     # -- row bookkeeping -----------------------------------------------------
     def band_rows(self, buf, b):
@@ -145,6 +204,19 @@ class ShardedExchange:
             for _ in range(max_order):
                 self.compute(prev, cur, self.e_total, 0, nb)
                 prev, cur = cur, prev
+        elif self.handles is not None:
+            # fused exchange: stage 2 stores into every rank's buffer, so one launch
+            # covers all bands and a single cross-rank barrier per order separates
+            # "all peers wrote E_k" from "E_k is read"
+            self._barrier()                      # every rank finished init()
+            for k in range(max_order):
+                if k > 0:
+                    self._barrier()
+                self.compute(prev, cur, self.e_total, 0, nb)
+                prev, cur = cur, prev
+            self._barrier()                      # all stores landed before buffers are reused
+            for b in range(nb):
+                self._all_gather_band(self.e_total, b)
         elif not self.cuda:
             for _ in range(max_order):
                 self.compute(prev, cur, self.e_total, 0, nb)

@@ -1,0 +1,49 @@
+"""Multi-GPU parity check (run under torchrun): the receiver-sharded exchange in
+every communication mode equals the single-GPU exchange computed on the same rank.
+
+    python -m torch.distributed.run --nproc-per-node 2 tools/check_sharded.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from sparrowpy_b200 import bake, distributed, exchange  # noqa: E402
+
+rank = int(os.environ["RANK"])
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+cfg = bench.CONFIGS[os.environ.get("CHECK_CONFIG", "c2s")]
+orders = 4
+ok = True
+for dtype in ("f64", "f32"):
+    rad = bench.build_scene(cfg, dtype)
+    n_samples = cfg["n_samples"]
+    tables = rad._pair_tables(bench.SPEED_OF_SOUND, bench.DT, n_samples)
+    delay0 = bake.delay_bins(rad._d0_dev, bench.SPEED_OF_SOUND, bench.DT)
+    ref = exchange.energy_exchange(tables, rad._e0_dev, delay0, n_samples, orders).dense().clone()
+    for mode in ("multicast", "p2p", "nccl"):
+        os.environ["SPB_COMM"] = mode
+        sx = distributed.ShardedExchange(tables, n_samples, dev)
+        for rep in range(2):                      # twice: buffer reuse across steps
+            sx.init(rad._e0_dev, delay0)
+            got = sx.run(orders).dense()
+            torch.cuda.synchronize()
+            same = bool(torch.equal(got, ref))
+            err = float((got - ref).abs().max() / ref.abs().max())
+            ok &= same
+            if rank == 0:
+                print(f"{dtype} {mode:9s} (ran as {sx.comm:9s}) rep {rep}: "
+                      f"equal={same} max rel diff {err:.2e}", flush=True)
+        del sx
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("SHARDED PARITY", "OK" if int(flag.item()) == 1 else "FAILED", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)

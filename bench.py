@@ -317,14 +317,25 @@ def main():
     # (tiled kernel: one FMA row per non-empty record slot = per kept directed pair)
     fma_launch = float(tables.src.numel()) * share * n_band * sx.t_pad / band_launches
     fma_tflops = 2.0 * fma_launch / (gather_avg_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+        traffic = tr.get(f"{args.config}/{args.dtype}/{args.gather}", {}).get("bytes")
+        if traffic is not None and world > 1:
+            traffic = None                      # captured at 1 GPU only
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None,
+                "frac": achieved / hbm_peak, "traffic": traffic,
                 "kernel": "k_gather_tma" if args.gather == "tma" else "k_gather",
                 "peak_source": peak_src, "avg_launch_ms": gather_avg_ms,
                 "launches_timed": len(gather_ms),
                 "share_of_step": sum(gather_ms) / max(elapsed_ms, 1e-9),
                 "executed_fma_tflops": fma_tflops,
                 "fma_pipe_nominal_tflops": 37.0 if code == _lib.F64 else 75.0,
+                "algorithmic_bytes_per_launch": alg_bytes_launch,
+                "binding_resource": "L1/shared-memory operand path (128 B/clk/SM): one "
+                                    "shifted operand per FMA; see profiles/ and DESIGN.md 3.1",
                 "note": "algorithmic bytes are those of the reference's dense-tilde "
                         "formulation; the factored kernel moves far fewer, so frac can "
                         "exceed 1 (see DESIGN.md)"}

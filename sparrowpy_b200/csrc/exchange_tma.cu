@@ -31,7 +31,7 @@ constexpr int kChunksT = kSliceT / 32;
 constexpr int kCtaT = kWarpsT * kSliceT;    // 1024 time bins per CTA
 constexpr int kBucket = 32;                 // delay bucket (bins) of one record
 constexpr int kWindow = kCtaT + kBucket;    // staged elements per record (max)
-constexpr int kStages = 7;
+constexpr int kStages = 12;
 template <typename T>
 struct alignas(16) TileRecord {
     T w[kR];             // weight per receiver slot (0 = no pair)

@@ -172,6 +172,7 @@ class ShardedExchange:
         senders), own shard only into e_total."""
         t = self.t
         self.e_b.zero_()
+        e0, delay0 = t.to_internal(e0), t.to_internal(delay0)
         if self.cuda:
             tdt = _lib.torch_dtype(t.dtype)
             _lib.call("spb_exchange_init", self.e_total, self.e_a, e0.to(tdt).contiguous(),
@@ -252,4 +253,4 @@ class ShardedExchange:
             for b in range(nb):
                 self._all_gather_band(self.e_total, b)
         return EnergyHistogram(self.e_total, t.n_patches, t.n_dirs, t.n_bands,
-                               self.n_samples, self.pad, n_alloc=self.n_alloc)
+                               self.n_samples, self.pad, n_alloc=self.n_alloc, tables=t)

@@ -33,6 +33,18 @@ class PairTables:
     ent_ptr: torch.Tensor = None   # (C*ceil(N/R) + 1,) int64  tiled records (TMA path)
     recs: torch.Tensor = None      # (n_records, record_bytes) uint8
     n_records: int = 0
+    rank: torch.Tensor = None      # (n_user,) int64 caller's patch id -> internal index
+    n_user: int = 0                # caller's patch count (n_patches is the internal one)
+
+    def to_internal(self, per_patch, dim=0):
+        """Reorder a per-patch tensor (patch axis ``dim``) into the internal patch
+        numbering; holes of the internal numbering are zero."""
+        if self.rank is None:
+            return per_patch
+        shape = list(per_patch.shape)
+        shape[dim] = self.n_patches
+        out = torch.zeros(shape, dtype=per_patch.dtype, device=per_patch.device)
+        return out.index_copy_(dim, self.rank, per_patch)
 
 
 def directed_pairs(pairs, ff_pairs, areas):
@@ -51,9 +63,17 @@ def directed_pairs(pairs, ff_pairs, areas):
 
 
 def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches,
-                      n_samples, dtype):
+                      n_samples, dtype, rank=None, n_internal=None):
     """Sort directed pairs into segments (class, receiver) and drop pairs whose
-    delay is >= n_samples (they contribute nothing, RadiosityFast.py:1137-1140)."""
+    delay is >= n_samples (they contribute nothing, RadiosityFast.py:1137-1140).
+
+    ``rank`` (optional, (N,) int64) renumbers the patches inside the exchange:
+    patch p becomes internal index ``rank[p] < n_internal`` (holes allowed).  The
+    exchange is invariant under a relabelling of patches; a spatially compact
+    numbering makes the 8 receivers of a tile close neighbours (more shared senders,
+    directions and delay bins per record).  Histograms come back in the caller's
+    numbering (EnergyHistogram.dense).
+    """
     code = _lib.dtype_code(dtype)
     tdt = _lib.torch_dtype(code)
     n_classes, n_dirs, n_bands = coef.shape
@@ -61,6 +81,11 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     keep = delay < n_samples
     sender, receiver, ff = sender[keep], receiver[keep], ff[keep]
     delay, out_dir, cls = delay[keep], out_dir[keep], cls[keep]
+    n_user = int(n_patches)
+    if rank is not None:
+        rank = rank.to(sender.device).long().contiguous()
+        n_patches = int(n_internal)
+        sender, receiver = rank[sender.long()], rank[receiver.long()]
     seg = cls.long() * n_patches + receiver.long()
     key = seg * n_patches + sender.long()
     order = torch.argsort(key)
@@ -74,6 +99,7 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     ent_ptr, recs = build_tile_records(sender, receiver, ff, delay, out_dir, cls, n_patches,
                                        n_dirs, n_classes, code)
     return PairTables(
+        rank=rank, n_user=n_user,
         ent_ptr=ent_ptr, recs=recs, n_records=int(recs.shape[0]),
         seg_ptr=seg_ptr.contiguous(), src=src.contiguous(),
         wgt=ff[order].to(tdt).contiguous(),
@@ -154,23 +180,36 @@ def build_tile_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_d
 
 class EnergyHistogram:
     """(patch, direction, band, time) histogram in the padded-row device layout:
-    ``data[(band * n_alloc + patch) * D + dir, PAD + t]``."""
+    ``data[(band * n_alloc + p) * D + dir, PAD + t]`` where ``p`` is the internal
+    patch index of the pair tables (``tables.rank`` maps the caller's ids to it)."""
 
-    def __init__(self, data, n_patches, n_dirs, n_bands, n_samples, pad, n_alloc=None):
+    def __init__(self, data, n_patches, n_dirs, n_bands, n_samples, pad, n_alloc=None,
+                 tables=None):
         self.data = data                    # (B * n_alloc * D, LD)
-        self.n_patches, self.n_dirs = n_patches, n_dirs
+        self.n_patches, self.n_dirs = n_patches, n_dirs      # internal patch count
         self.n_bands, self.n_samples, self.pad = n_bands, n_samples, pad
         self.n_alloc = n_patches if n_alloc is None else n_alloc
+        self.tables = tables
 
     @property
     def ld(self):
         return self.data.shape[1]
 
+    @property
+    def rank(self):
+        return None if self.tables is None else self.tables.rank
+
     def dense(self):
-        """(N, D, B, T) view in the reference's axis order (device, strided)."""
+        """(N, D, B, T) in the reference's axis order and the caller's patch numbering
+        (on the device; a strided view when no patch relabelling is active)."""
         v = self.data.view(self.n_bands, self.n_alloc, self.n_dirs, self.ld)
         v = v[:, :self.n_patches, :, self.pad:self.pad + self.n_samples]
+        if self.rank is not None:
+            v = v.index_select(1, self.rank)
         return v.permute(1, 2, 0, 3)
+
+    def to_internal(self, per_patch, dim):
+        return per_patch if self.tables is None else self.tables.to_internal(per_patch, dim)
 
 
 class ExchangeWorkspace:
@@ -204,6 +243,7 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
     tdt = _lib.torch_dtype(t.dtype)
     device = e0.device
     ws = workspace or ExchangeWorkspace(t, n_samples, device, need_orders=max_order >= 1)
+    e0, delay0 = t.to_internal(e0), t.to_internal(delay0)
     e0 = e0.to(tdt).contiguous()
     delay0 = delay0.to(torch.int32).contiguous()
     use_tiles = t.recs is not None and os.environ.get("SPB_GATHER", "tma") != "csr"
@@ -212,7 +252,8 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
               t.n_patches, t.n_classes, t.n_dirs, t.n_bands, n_samples, ws.t_pad, ws.pad,
               int(max_order), ws.e_total, ws.e_a, ws.e_b, ws.g, _lib.I32(t.dtype),
               _lib.stream_ptr())
-    return EnergyHistogram(ws.e_total, t.n_patches, t.n_dirs, t.n_bands, n_samples, ws.pad)
+    return EnergyHistogram(ws.e_total, t.n_patches, t.n_dirs, t.n_bands, n_samples, ws.pad,
+                           tables=t)
 
 
 def collect_mono(hist, rdir, shift, scale, n_split=None):
@@ -224,6 +265,7 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
     n_rcv = rdir.shape[0]
     tdt = hist.data.dtype
     code = _lib.dtype_code(tdt)
+    rdir, shift, scale = (hist.to_internal(x, 1) for x in (rdir, shift, scale))
     if n_split is None:
         n_split = max(1, min(64, hist.n_patches // 256))
     out = torch.empty((n_rcv, hist.n_bands, hist.n_samples), dtype=tdt,
@@ -249,12 +291,15 @@ def collect_patchwise(hist, rdir, shift, scale):
     n_rcv = rdir.shape[0]
     tdt = hist.data.dtype
     code = _lib.dtype_code(tdt)
+    rdir, shift, scale = (hist.to_internal(x, 1) for x in (rdir, shift, scale))
     out = torch.empty((n_rcv, hist.n_patches, hist.n_bands, hist.n_samples), dtype=tdt,
                       device=hist.data.device)
     _lib.call("spb_collect_patchwise", hist.data, rdir.contiguous(), shift.contiguous(),
               scale.to(tdt).contiguous(), n_rcv, hist.n_patches, hist.n_alloc, hist.n_dirs,
               hist.n_bands, hist.n_samples, hist.ld, hist.pad, out, _lib.I32(code),
               _lib.stream_ptr())
+    if hist.rank is not None:
+        out = out.index_select(1, hist.rank)
     return out
 
 

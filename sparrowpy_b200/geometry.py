@@ -137,3 +137,37 @@ def calculate_area(points):
         nrm = np.sqrt((cl[:, 0] * cl[:, 0] + cl[:, 1] * cl[:, 1]) + cl[:, 2] * cl[:, 2])
         area = area + .5 * nrm.astype(np.float64)
     return area
+
+
+def compact_patch_order(patches_points, patch_to_wall_ids, block=(2, 4)):
+    """Internal patch numbering in which every run of 8 consecutive indices is a
+    compact ``block`` (2 x 4 patches) of one wall instead of an 8 x 1 strip.
+
+    Used only to lay out the receiver tiles of the energy-exchange kernel (any
+    numbering gives the same result).  Blocks at the rim of a wall grid are not full,
+    so the internal index space has holes: returns ``(rank, n_internal)`` with
+    ``rank[patch] = internal index`` and ``n_internal = 8 * number of blocks >= N``.
+    """
+    pts = np.asarray(patches_points, dtype=float)
+    ids = np.asarray(patch_to_wall_ids)
+    center = pts.mean(axis=1)
+    per = block[0] * block[1]
+    rank = np.empty(len(ids), dtype=np.int64)
+    base = 0
+    for w in np.unique(ids):
+        sel = np.nonzero(ids == w)[0]
+        ext = pts[sel].max(axis=(0, 1)) - pts[sel].min(axis=(0, 1))
+        axes = sorted(np.argsort(ext)[1:])               # the two in-plane axes
+        size = (pts[sel].max(axis=1) - pts[sel].min(axis=1)).max(axis=0)
+        idx = []
+        for ax in axes:
+            step = size[ax] if size[ax] > 0 else 1.0
+            idx.append(np.rint((center[sel, ax] - center[sel, ax].min()) / step).astype(
+                np.int64))
+        nb1 = int(idx[1].max()) // block[1] + 1
+        blk = (idx[0] // block[0]) * nb1 + idx[1] // block[1]
+        within = (idx[0] % block[0]) * block[1] + idx[1] % block[1]
+        rank[sel] = base + blk * per + within
+        base += (int(blk.max()) + 1) * per
+    assert len(np.unique(rank)) == len(rank)
+    return rank, int(base)

@@ -317,9 +317,12 @@ class DirectionalRadiosityFast:
             b = self._baked
             delay = bake.delay_bins(b["dist"], speed_of_sound, dt).long()
             delay = torch.stack([delay, delay], dim=1).reshape(-1)
+            rank, n_internal = geometry.compact_patch_order(
+                self._patches_points, self._patch_to_wall_ids)
             tables = exchange.build_pair_tables(
                 b["sender"], b["receiver"], b["ff_dir"], delay, b["out_dir"], b["cls"],
-                b["coef"], self.n_patches, n_samples, self._dtype)
+                b["coef"], self.n_patches, n_samples, self._dtype,
+                rank=torch.from_numpy(rank).to(self._device), n_internal=n_internal)
             self._tables = (key, tables)
         return self._tables[1]
 

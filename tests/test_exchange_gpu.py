@@ -226,3 +226,60 @@ def test_sharded_driver_matches_one_call_api(oracle):
     got2 = exchange.EnergyHistogram(sx.e_total, n, t.n_dirs, t.n_bands, n_samples, sx.pad,
                                     n_alloc=sx.n_alloc).dense()
     assert torch.equal(got2, ref)
+
+
+def test_exchange_invariant_under_patch_renumbering(oracle):
+    """Any internal patch numbering (with holes) gives the same histogram and the
+    same receiver ETC in the caller's numbering."""
+    from sparrowpy_b200 import exchange
+    g = load_golden("scene_directional")
+    out = oracle_run(oracle, g)
+    dev = torch.device("cuda:0")
+    n_samples = out["etc"].shape[-1]
+    base = device_tables(g, out, "f64", n_samples)
+    n = base.n_patches
+    e0 = torch.from_numpy(out["energy_init_source"]).to(dev)
+    c, dt = float(g["speed_of_sound"]), float(g["dt"])
+    delay0 = torch.from_numpy(
+        (out["distance_patches_to_source"] / c / dt).astype(np.int32)).to(dev)
+    ref = exchange.energy_exchange(base, e0, delay0, n_samples, 4)
+    gen = np.random.default_rng(11)
+    n_int = n + 37
+    rank = torch.from_numpy(np.sort(gen.choice(n_int, n, replace=False))[gen.permutation(n)])
+
+    # rebuild the tables with the renumbering (same inputs as device_tables)
+    import sparrowpy_b200.exchange as ex
+    pairs = torch.from_numpy(out["visible_patches"]).to(dev)
+    ff = torch.from_numpy(out["ff_pairs"]).to(dev)
+    areas = torch.from_numpy(out["patches_area"]).to(dev)
+    sender, receiver, ffd = ex.directed_pairs(pairs, ff, areas)
+    s_in = g["vi"].shape[1]
+    brdf = g["brdf"].reshape(g["brdf"].shape[0], s_in, g["vo"].shape[1], -1)
+    wall = torch.from_numpy(out["patch_to_wall_ids"]).to(dev)
+    cls = torch.from_numpy(g["brdf_index"]).to(dev)[wall[sender]] * s_in + \
+        torch.from_numpy(out["in_dir"]).to(dev)
+    coef = torch.from_numpy(np.exp(-g["air_attenuation"])[None, None, :] * brdf.reshape(
+        -1, brdf.shape[2], brdf.shape[3])).to(dev)
+    tables = ex.build_pair_tables(
+        sender, receiver, ffd, torch.from_numpy(out["pair_delays"]).to(dev),
+        torch.from_numpy(out["out_dir"]).to(dev), cls, coef, n, n_samples, "f64",
+        rank=rank.to(dev), n_internal=n_int)
+    assert tables.n_patches == n_int and tables.n_user == n
+    got = exchange.energy_exchange(tables, e0, delay0, n_samples, 4)
+    a, b = got.dense(), ref.dense()
+    assert a.shape == b.shape
+    assert float((a - b).abs().max() / b.abs().max()) < 1e-13
+    # receiver collection takes per-patch inputs in the caller's numbering
+    air, rcv, cen = g["air_attenuation"], g["receivers"], out["patches_center"]
+    dist = np.sqrt(((cen[None] - rcv[:, None]) ** 2).sum(-1))
+    scale = torch.from_numpy(out["receiver_factor"][:, :, None] *
+                             np.exp(-air[None, None, :] * dist[:, :, None])).to(dev)
+    shift = torch.from_numpy(np.mod(out["receiver_delays"], n_samples).astype(np.int32)).to(dev)
+    rdir = torch.from_numpy(out["receiver_dir_index"].astype(np.int32)).to(dev)
+    m1 = exchange.collect_mono(got, rdir, shift, scale)
+    m0 = exchange.collect_mono(ref, rdir, shift, scale)
+    assert float((m1 - m0).abs().max() / m0.abs().max()) < 1e-12
+    p1 = exchange.collect_patchwise(got, rdir, shift, scale)
+    p0 = exchange.collect_patchwise(ref, rdir, shift, scale)
+    assert p1.shape == p0.shape
+    assert float((p1 - p0).abs().max() / p0.abs().max()) < 1e-12

@@ -111,11 +111,20 @@ struct StoreTargets {
     int n;
 };
 
-__device__ __forceinline__ void multimem_store(double *addr, double v) {
-    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
-}
-__device__ __forceinline__ void multimem_store(float *addr, float v) {
-    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+// 16-byte vectors: every stage-2 thread owns 16/sizeof(T) consecutive time bins, so
+// local, peer and multicast stores are all 128-bit
+template <typename T>
+struct alignas(16) Vec16 {
+    static constexpr int kN = 16 / sizeof(T);
+    T v[kN];
+};
+
+template <typename T>
+__device__ __forceinline__ void multimem_store16(T *addr, const Vec16<T> &x) {
+    const float *f = reinterpret_cast<const float *>(&x);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr),
+                 "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
+                 : "memory");
 }
 
 template <typename T, int MODE>
@@ -125,36 +134,48 @@ k_mix(const T *__restrict__ g, StoreTargets<T> cur, T *__restrict__ e_total,
       int64_t n_patches, int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
       int64_t n_bands, int64_t b_lo, int64_t j_lo, int64_t n_j, int64_t t_pad, int64_t ld,
       int64_t pad) {
+    constexpr int kV = Vec16<T>::kN;
     const int64_t jb = blockIdx.x;
     const int64_t b = b_lo + jb / n_j;
     const int64_t j = j_lo + jb % n_j;
-    const int64_t t = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t t = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * kV;
     if (t >= t_pad) return;
     for (int64_t d0 = 0; d0 < n_dirs; d0 += kMixDirs) {
-        T acc[kMixDirs];
+        Vec16<T> acc[kMixDirs];
 #pragma unroll
-        for (int dd = 0; dd < kMixDirs; ++dd) acc[dd] = T(0);
+        for (int dd = 0; dd < kMixDirs; ++dd)
+#pragma unroll
+            for (int q = 0; q < kV; ++q) acc[dd].v[q] = T(0);
         for (int64_t c = 0; c < n_classes; ++c) {
             const int64_t seg = c * n_patches + j;
             if (seg_ptr[seg] == seg_ptr[seg + 1]) continue;   // CTA-uniform
-            const T gv = g[(b * n_classes * n_patches + seg) * ld + pad + t];
+            const Vec16<T> gv = *reinterpret_cast<const Vec16<T> *>(
+                g + (b * n_classes * n_patches + seg) * ld + pad + t);
             const T *cf = coef + (c * n_dirs + d0) * n_bands + b;
 #pragma unroll
             for (int dd = 0; dd < kMixDirs; ++dd)
-                if (d0 + dd < n_dirs) acc[dd] = fma(cf[dd * n_bands], gv, acc[dd]);
+                if (d0 + dd < n_dirs) {
+                    const T w = cf[dd * n_bands];
+#pragma unroll
+                    for (int q = 0; q < kV; ++q) acc[dd].v[q] = fma(w, gv.v[q], acc[dd].v[q]);
+                }
         }
 #pragma unroll
         for (int dd = 0; dd < kMixDirs; ++dd) {
             if (d0 + dd < n_dirs) {
                 const int64_t o = ((b * n_alloc + j) * n_dirs + d0 + dd) * ld + pad + t;
                 if (MODE == kStoreLocal) {
-                    cur.ptr[0][o] = acc[dd];
+                    *reinterpret_cast<Vec16<T> *>(cur.ptr[0] + o) = acc[dd];
                 } else if (MODE == kStorePeers) {
-                    for (int p = 0; p < cur.n; ++p) cur.ptr[p][o] = acc[dd];
+                    for (int p = 0; p < cur.n; ++p)
+                        *reinterpret_cast<Vec16<T> *>(cur.ptr[p] + o) = acc[dd];
                 } else {
-                    multimem_store(cur.mc + o, acc[dd]);
+                    multimem_store16(cur.mc + o, acc[dd]);
                 }
-                e_total[o] += acc[dd];
+                Vec16<T> tot = *reinterpret_cast<Vec16<T> *>(e_total + o);
+#pragma unroll
+                for (int q = 0; q < kV; ++q) tot.v[q] += acc[dd].v[q];
+                *reinterpret_cast<Vec16<T> *>(e_total + o) = tot;
             }
         }
     }
@@ -261,7 +282,7 @@ int mix_t(const void *g, const StoreTargets<T> &cur, int mode, void *e_total,
     const int64_t n_j = j_hi - j_lo, n_b = b_hi - b_lo;
     if (n_j * n_b == 0) return 0;
     SPB_REQUIRE(n_j * n_b <= 2147483647LL, "too many (patch, band) rows");
-    dim3 grid((unsigned)(n_j * n_b), (unsigned)ceil_div(t_pad, 256));
+    dim3 grid((unsigned)(n_j * n_b), (unsigned)ceil_div(t_pad, 256 * Vec16<T>::kN));
 #define SPB_MIX_LAUNCH(MODE)                                                                \
     k_mix<T, MODE><<<grid, 256, 0, st>>>((const T *)g, cur, (T *)e_total, seg_ptr,          \
                                          (const T *)coef, n_patches, n_alloc, n_classes,    \

@@ -20,8 +20,7 @@ patches own no pairs and stay zero.
 
 Communication modes (``SPB_COMM``):
 
-``multicast`` (default when the symmetric allocation has a multicast address) and
-``p2p``: the ping-pong buffers are torch symmetric-memory allocations mapped into
+``p2p`` (default) and ``multicast``: the ping-pong buffers are torch symmetric-memory allocations mapped into
 every rank; stage 2 (``spb_exchange_mix_fused``) stores each ``E_k`` element of the
 rank's receivers directly into all ranks' buffers -- one NVSwitch multicast store
 (``multimem.st``) or one NVLink P2P store per peer -- so the all-gather is fused into
@@ -79,10 +78,9 @@ class ShardedExchange:
         self.handles = None
         if self.world > 1:
             # P2P stores cost (world-1) x the shard in NVLink egress, a multicast store
-            # 1 x (the switch replicates) but also routes the local copy through the
-            # switch: P2P wins for 2 ranks, multicast beyond
-            default = "p2p" if self.world <= 2 else "multicast"
-            self.comm = os.environ.get("SPB_COMM", default) if self.cuda else "gloo"
+            # 1 x (the switch replicates); measured on this pool (2 and 4 GPUs, C2) the
+            # multimem.st path is nevertheless 10-20 % slower, so P2P is the default
+            self.comm = os.environ.get("SPB_COMM", "p2p") if self.cuda else "gloo"
         if self.comm in ("multicast", "p2p"):
             try:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -111,6 +109,8 @@ class ShardedExchange:
         self.compute = compute or self._cuda_order
         self.comm_stream = torch.cuda.Stream(device=device) if (
             self.cuda and self.comm == "nccl") else None
+        self.side_stream = torch.cuda.Stream(device=device) if (
+            self.cuda and self.handles is not None) else None
 
     # -- local kernels -------------------------------------------------------
     def _cuda_order(self, prev, cur, total, b_lo, b_hi):
@@ -146,8 +146,8 @@ class ShardedExchange:
                   t.n_bands, b_lo, b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad,
                   code, st)
 
-    def _barrier(self):
-        next(iter(self.handles.values())).barrier(0)
+    def _barrier(self, channel=0):
+        next(iter(self.handles.values())).barrier(channel)
 
     # -- row bookkeeping -----------------------------------------------------
     def band_rows(self, buf, b):
@@ -206,15 +206,25 @@ class ShardedExchange:
                 self.compute(prev, cur, self.e_total, 0, nb)
                 prev, cur = cur, prev
         elif self.handles is not None:
-            # fused exchange: stage 2 stores into every rank's buffer, so one launch
-            # covers all bands and a single cross-rank barrier per order separates
-            # "all peers wrote E_k" from "E_k is read"
+            # fused exchange: stage 2 stores into every rank's buffer; a cross-rank
+            # barrier per order separates "all peers wrote E_k" from "E_k is read".
+            # The bands are split into two groups on two streams so that one group's
+            # store-bound stage 2 (NVLink) overlaps the other group's stage 1 (SMs).
+            main = torch.cuda.current_stream()
+            groups = [(0, nb)] if nb < 2 else [(0, (nb + 1) // 2), ((nb + 1) // 2, nb)]
+            streams = [main, self.side_stream][:len(groups)]
             self._barrier()                      # every rank finished init()
+            for st in streams[1:]:
+                st.wait_stream(main)
             for k in range(max_order):
-                if k > 0:
-                    self._barrier()
-                self.compute(prev, cur, self.e_total, 0, nb)
+                for gi, (b0, b1) in enumerate(groups):
+                    with torch.cuda.stream(streams[gi]):
+                        if k > 0:
+                            self._barrier(gi)
+                        self.compute(prev, cur, self.e_total, b0, b1)
                 prev, cur = cur, prev
+            for st in streams[1:]:
+                main.wait_stream(st)
             self._barrier()                      # all stores landed before buffers are reused
             for b in range(nb):
                 self._all_gather_band(self.e_total, b)

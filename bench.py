@@ -182,6 +182,47 @@ def cpu_exchange_rate(rad, cfg, n_threads, budget_s=12.0, log=None):
                         f"and orders; fixed per-order passes {t_fixed:.2f}s included"))
 
 
+def time_bake(rad, n_pairs):
+    """Device times of the two compute-bound bake kernels on the baked scene (north_star
+    (1)), as fractions of the FP64 pipe from the nominal op counts of SURVEY.md 8d:
+    ~350 flop per full (pair, blocker) visibility test but ~25 for the fast path that
+    decides almost all of them, ~3.3 kflop per Stokes pair."""
+    import torch
+    from sparrowpy_b200 import bake
+    g = rad._geom()
+
+    def timed(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps
+
+    n = rad.n_patches
+    blockers = bake.make_blockers(g["points"], g["normal"])
+    vis = torch.empty((n, n), dtype=torch.uint8, device=g["center"].device)
+    from sparrowpy_b200 import _lib
+    vis_ms = timed(lambda: _lib.call("spb_visibility_p2p", g["center"], n, blockers, n, vis,
+                                     _lib.stream_ptr()), reps=1)
+    pairs = rad._baked["pairs"]
+    ff_ms = timed(lambda: bake.form_factors(g["points"], g["normal"], g["area"], pairs))
+    pair_blocker = 0.5 * n * (n - 1) * n
+    fp64_peak = 37e12
+    return {
+        "visibility_ms": vis_ms, "pair_blocker_tests_per_s": pair_blocker / (vis_ms * 1e-3),
+        "visibility_fp64_frac_nominal": 25.0 * pair_blocker / (vis_ms * 1e-3) / fp64_peak,
+        "form_factor_ms": ff_ms, "form_factor_pairs_per_s": n_pairs / (ff_ms * 1e-3),
+        "form_factor_fp64_frac_nominal": 3300.0 * n_pairs / (ff_ms * 1e-3) / fp64_peak,
+        "fp64_pipe_nominal_tflops": 37.0,
+        "note": "pair_blocker counts every (i<j, blocker) combination, including those "
+                "skipped by the early exit once a pair is known to be blocked",
+    }
+
+
 # ---------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -234,6 +275,7 @@ def main():
     n_samples, orders = cfg["n_samples"], cfg["orders"]
     tables = rad._pair_tables(SPEED_OF_SOUND, DT, n_samples)
     n_pairs = int(rad._baked["pairs"].shape[0])
+    bake_info = time_bake(rad, n_pairs) if rank == 0 else None
     n_dir, n_band = tables.n_dirs, tables.n_bands
     x_per_step = 2.0 * n_pairs * n_samples * orders
     code = _lib.dtype_code(args.dtype)
@@ -398,6 +440,8 @@ def main():
                                        if world > 1 else "1 GPU")},
             "clocks": clocks.summary(), "roofline": roofline,
         }
+        if bake_info:
+            line["bake"] = bake_info
         if e2e:
             line["e2e"] = e2e
         if cpu:

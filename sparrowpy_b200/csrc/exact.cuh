@@ -114,10 +114,18 @@ __device__ inline void make_blocker(const double *pts /*4x3*/, const double *n, 
 // evaluation: b keeps the y of the query point and b_x > pt_x, so a query point
 // above/below the polygon's y-range or right of its x-range (by more than h)
 // cannot register a hit on any side -> count == 0 -> False.
+// point_in_polygon_2d is the part after the coplanarity test
+// |DOT(p - S0, n)| <= eta (geometry.py:641).
+__device__ inline bool point_in_polygon_2d(const double *p, const Blocker &k);
+
 __device__ inline bool point_in_polygon(const double *p, const Blocker &k) {
     double d0[3];
     sub3(p, k.s0, d0);
     if (fabs(dot3(d0, k.n)) > kEta) return false;
+    return point_in_polygon_2d(p, k);
+}
+
+__device__ inline bool point_in_polygon_2d(const double *p, const Blocker &k) {
     const double pt[2] = {dot3(k.r0, p), dot3(k.r1, p)};
     if (pt[1] > k.ymax + k.h || pt[1] < k.ymin - k.h || pt[0] > k.xmax + k.h) return false;
     int count = 0;
@@ -146,44 +154,18 @@ __device__ inline bool point_in_polygon(const double *p, const Blocker &k) {
     return count != 0;
 }
 
-// geometry.py:841-909: is the segment A-B blocked by this surface?
-// Literal evaluation, used for every case the fast filter cannot decide.
-__device__ inline bool blocked_full(const double *A, const double *B, const Blocker &k) {
-    const bool inA = point_in_polygon(A, k);
-    const bool inB = point_in_polygon(B, k);
-    double d[3];
-    if (!inA && !inB) {
-        double v[3];
-        sub3(B, A, v);
-        const double dp = dot3(v, k.n);
-        if (!(fabs(dp) > 1e-6)) return false;
-        double w[3];
-        sub3(B, k.s0, w);
-        const double fac = -(dot3(k.n, w) / dp);
-        const double pt[3] = {(w[0] + k.s0[0]) + fac * v[0], (w[1] + k.s0[1]) + fac * v[1],
-                              (w[2] + k.s0[2]) + fac * v[2]};
-        if (!point_in_polygon(pt, k)) return false;
-        double pa[3], pb[3];
-        sub3(pt, A, pa);
-        sub3(pt, B, pb);
-        return dot3(pa, pb) < 0;
-    } else if (inA && !inB && (sub3(B, A, d), dot3(k.n, d) < 0)) {
-        return true;
-    } else if (!inA && inB && (sub3(A, B, d), dot3(k.n, d) < 0)) {
-        return true;
-    } else {
-        double da[3], db[3];
-        sub3(A, k.s0, da);
-        sub3(B, k.s0, db);
-        return fabs(dot3(da, k.n)) < kEta && fabs(dot3(db, k.n)) < kEta && (inA || inB);
-    }
-}
-
-// Fast, result-preserving front end of blocked_full for the common case.
-//   v = B - A, vv = |v|^2 (any rounding).
-// Order of evaluation differs from the reference, the value does not: the
-// predicates are pure, and the only shortcut (skipping the polygon test when the
-// plane hit lies clearly outside the open segment) is justified below.
+// geometry.py:841-909 evaluated for one blocking surface, organised so that the
+// common cases cost ~20 FP64 operations.  Only the ORDER of evaluation differs from
+// the reference; the predicates are pure, so the value cannot:
+//  * inA / inB start with the coplanarity test (geometry.py:641), whose dot products
+//    dA, dB are needed anyway (dB is also the numerator of the plane hit parameter);
+//  * in the first branch (neither end point in the surface, :881-893) the reference
+//    requires  hit exists  AND  hit in polygon  AND  (hit-A).(hit-B) < 0.  The hit is
+//    B + fac*v (+ rounding ~1e-13) with fac = -(dB/dp), so (hit-A).(hit-B) =
+//    fac(1+fac)|v|^2 is positive whenever fac lies outside [-1, 0] by a margin; that
+//    margin test is done on products (no division) with thresholds 2e-3 / -1.002,
+//    which imply fac > 1e-3 resp. fac < -1.001 for the rounded quotient as well.
+//    v = B - A, cull_ok = |v|^2 > 1e-6.
 __device__ __forceinline__ bool blocked(const double *A, const double *B, const double *v,
                                         bool cull_ok, const Blocker &k) {
     double wa[3], w[3];
@@ -191,14 +173,19 @@ __device__ __forceinline__ bool blocked(const double *A, const double *B, const 
     sub3(B, k.s0, w);
     const double dA = dot3(wa, k.n);
     const double dB = dot3(w, k.n);
-    if (fabs(dA) > kEta && fabs(dB) > kEta) {
-        // neither end point lies in the surface's plane -> inA = inB = False
+    bool inA = false, inB = false;
+    if (!(fabs(dA) > kEta)) inA = point_in_polygon_2d(A, k);
+    if (!(fabs(dB) > kEta)) inB = point_in_polygon_2d(B, k);
+    if (!inA && !inB) {
         const double dp = dot3(v, k.n);
         if (!(fabs(dp) > 1e-6)) return false;               // geometry.py:599-604
+        if (cull_ok) {
+            const double u = -dB;
+            const bool outside = dp > 0 ? (u > 2e-3 * dp || u < -1.002 * dp)
+                                        : (u < 2e-3 * dp || u > -1.002 * dp);
+            if (outside) return false;
+        }
         const double fac = -(dB / dp);
-        // pt = B + fac*v (+ rounding ~1e-13): (pt-A).(pt-B) = fac(1+fac)|v|^2 > 0
-        // whenever fac is outside [-1, 0] by the margin -> not blocked.
-        if (cull_ok && (fac > 1e-3 || fac < -1.001)) return false;
         const double pt[3] = {(w[0] + k.s0[0]) + fac * v[0], (w[1] + k.s0[1]) + fac * v[1],
                               (w[2] + k.s0[2]) + fac * v[2]};
         double pa[3], pb[3];
@@ -207,7 +194,10 @@ __device__ __forceinline__ bool blocked(const double *A, const double *B, const 
         if (!(dot3(pa, pb) < 0)) return false;
         return point_in_polygon(pt, k);
     }
-    return blocked_full(A, B, k);
+    double d[3];
+    if (inA && !inB && (sub3(B, A, d), dot3(k.n, d) < 0)) return true;      // :895-897
+    if (!inA && inB && (sub3(A, B, d), dot3(k.n, d) < 0)) return true;      // :899-901
+    return fabs(dA) < kEta && fabs(dB) < kEta;                              // :903-906
 }
 
 // numba `diff /= np.linalg.norm(diff)` followed by argmin of squared distances

@@ -39,11 +39,40 @@ __global__ void k_make_blockers(const double *__restrict__ pts,
 // visibility: geometry.py:750-839
 // ---------------------------------------------------------------------------
 constexpr int kVisThreads = 128;
-constexpr int kVisTile = 32;      // blockers staged in shared memory per step
+constexpr int kVisTile = 64;      // blockers staged in shared memory per step
+
+// Per-blocker data of the fast path, rebuilt per CTA while a tile is staged: the
+// view point A is the same for every thread of the CTA (row i / the evaluation
+// point), so everything that depends on (A, blocker) only is computed once per
+// (CTA, blocker) instead of once per thread.
+struct BlockerHead {
+    double n[3];
+    double s0[3];
+    double dA;          // DOT(A - S0, n), exactly as exact::blocked computes it
+    double cop_a;       // 1.0 when |dA| <= eta (A lies in the blocker's plane)
+    double clr_a;       // exact::ray_clearance of A's in-plane projection
+    double pad_;
+};
+constexpr int kHeadDoubles = sizeof(BlockerHead) / sizeof(double);
+
+__device__ __noinline__ bool blocked_slow(const double *A, const double *B, const double *v,
+                                          double vlen, bool cull_ok, const Blocker *k) {
+    return exact::blocked(A, B, v, vlen, cull_ok, *k);
+}
 
 // Shared loop: AND over all blockers of "not blocked", staged through smem.
 // `first_a/first_b`: blocker indices tested first (or -1) -- only an ordering
 // heuristic, the conjunction does not depend on order.
+//
+// The inner loop decides the common cases inline with the rules proved in
+// exact::blocked (same arithmetic for every value the reference compares):
+//   * neither end point in the blocker's plane: no plane hit (|dp| <= 1e-6) or hit
+//     parameter clearly outside the open segment (rule (a));
+//   * an end point in the plane with positive exact::ray_clearance: it is not "in the
+//     surface"; if the other end is off the plane the hit lies within eta*|v|/|dp| of
+//     that end point and misses the polygon too when the clearance exceeds that
+//     distance (rule (b)); if both ends are in the plane there is no plane hit.
+// Everything else goes to exact::blocked.
 __device__ __forceinline__ bool visible_against_all(const double *A, const double *B,
                                                     bool active,
                                                     const Blocker *__restrict__ blockers,
@@ -52,20 +81,74 @@ __device__ __forceinline__ bool visible_against_all(const double *A, const doubl
     double v[3];
     exact::sub3(B, A, v);
     const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double vlen = sqrt(vv);
     const bool cull_ok = vv > 1e-6;            // see exact::blocked
     bool visible = active;
-    if (visible && first_a >= 0) visible = !exact::blocked(A, B, v, cull_ok, blockers[first_a]);
-    if (visible && first_b >= 0) visible = !exact::blocked(A, B, v, cull_ok, blockers[first_b]);
+    if (visible && first_a >= 0)
+        visible = !blocked_slow(A, B, v, vlen, cull_ok, blockers + first_a);
+    if (visible && first_b >= 0)
+        visible = !blocked_slow(A, B, v, vlen, cull_ok, blockers + first_b);
     const Blocker *tile = reinterpret_cast<const Blocker *>(sm);
+    BlockerHead *heads = reinterpret_cast<BlockerHead *>(sm + kVisTile * kBlockerDoubles);
     for (int64_t s0 = 0; s0 < m; s0 += kVisTile) {
         if (!__syncthreads_or(visible)) break;          // whole CTA decided
         const int cnt = (int)min((int64_t)kVisTile, m - s0);
         const double *src = reinterpret_cast<const double *>(blockers + s0);
         for (int k = threadIdx.x; k < cnt * kBlockerDoubles; k += blockDim.x) sm[k] = src[k];
+        if ((int)threadIdx.x < cnt) {
+            const Blocker &bk = blockers[s0 + threadIdx.x];
+            BlockerHead h;
+            double wa[3];
+            for (int c = 0; c < 3; ++c) { h.n[c] = bk.n[c]; h.s0[c] = bk.s0[c]; }
+            exact::sub3(A, h.s0, wa);
+            h.dA = exact::dot3(wa, h.n);
+            h.cop_a = (fabs(h.dA) > exact::kEta) ? 0.0 : 1.0;
+            h.clr_a = exact::ray_clearance(exact::dot3(bk.r0, A), exact::dot3(bk.r1, A), bk);
+            h.pad_ = 0.0;
+            heads[threadIdx.x] = h;
+        }
         __syncthreads();
         if (visible) {
             for (int s = 0; s < cnt; ++s) {
-                if (exact::blocked(A, B, v, cull_ok, tile[s])) { visible = false; break; }
+                const BlockerHead &h = heads[s];
+                double w[3];
+                exact::sub3(B, h.s0, w);
+                const double dB = exact::dot3(w, h.n);
+                const double dp = exact::dot3(v, h.n);
+                const bool cop_a = h.cop_a != 0.0;
+                const bool cop_b = !(fabs(dB) > exact::kEta);
+                const bool hit = fabs(dp) > 1e-6;
+                bool decided = false;          // "not blocked" by the inline rules
+                if (!cop_a && !cop_b) {
+                    decided = !hit;
+                } else {
+                    double clr_b = 1.0;
+                    if (cop_b) {
+                        const Blocker &bk = tile[s];
+                        clr_b = exact::ray_clearance(exact::dot3(bk.r0, B),
+                                                     exact::dot3(bk.r1, B), bk);
+                    }
+                    const double clr_a = cop_a ? h.clr_a : 1.0;
+                    if (clr_a > exact::kClearGuard && clr_b > exact::kClearGuard) {
+                        // neither end point is in the surface
+                        if (!hit) decided = true;
+                        else if (cull_ok && (cop_a != cop_b)) {
+                            const double slack = exact::kEta * vlen / fabs(dp) + 3e-9;
+                            decided = (cop_a ? clr_a : clr_b) > slack;
+                        }
+                    }
+                }
+                if (!decided && hit && cull_ok) {           // rule (a)
+                    const double u = -dB;
+                    const bool outside = dp > 0 ? (u > 2e-3 * dp || u < -1.002 * dp)
+                                                : (u < 2e-3 * dp || u > -1.002 * dp);
+                    // only valid when neither end point is in the surface
+                    decided = outside && !cop_a && !cop_b;
+                }
+                if (!decided && blocked_slow(A, B, v, vlen, cull_ok, tile + s)) {
+                    visible = false;
+                    break;
+                }
             }
         }
     }
@@ -77,7 +160,7 @@ __global__ void __launch_bounds__(kVisThreads)
 k_vis_p2p(const double *__restrict__ centers, int64_t n,
           const Blocker *__restrict__ blockers, int64_t m, int64_t chunks_per_row,
           uint8_t *__restrict__ vis) {
-    __shared__ double sm[kVisTile * kBlockerDoubles];
+    __shared__ double sm[kVisTile * (kBlockerDoubles + kHeadDoubles)];
     const int64_t i = blockIdx.x / chunks_per_row;
     const int64_t j0 = (blockIdx.x % chunks_per_row) * kVisThreads;
     if (j0 + kVisThreads - 1 <= i) return;               // chunk entirely at j <= i
@@ -99,7 +182,7 @@ __global__ void __launch_bounds__(kVisThreads)
 k_vis_pt2p(const double *__restrict__ points, const double *__restrict__ centers, int64_t n,
            const Blocker *__restrict__ blockers, int64_t m, int64_t chunks_per_row,
            uint8_t *__restrict__ vis) {
-    __shared__ double sm[kVisTile * kBlockerDoubles];
+    __shared__ double sm[kVisTile * (kBlockerDoubles + kHeadDoubles)];
     const int64_t r = blockIdx.x / chunks_per_row;
     const int64_t j = (blockIdx.x % chunks_per_row) * kVisThreads + threadIdx.x;
     const bool active = j < n;
@@ -511,7 +594,7 @@ __global__ void k_probe_basic_visibility(const double *__restrict__ A,
     exact::sub3(b, a, v);
     const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
     const Blocker blk = blockers[k];
-    visible[k] = exact::blocked(a, b, v, vv > 1e-6, blk) ? 0 : 1;
+    visible[k] = exact::blocked(a, b, v, sqrt(vv), vv > 1e-6, blk) ? 0 : 1;
     in_a[k] = exact::point_in_polygon(a, blk) ? 1 : 0;
     in_b[k] = exact::point_in_polygon(b, blk) ? 1 : 0;
 }

@@ -74,8 +74,9 @@ struct Blocker {
     double p2[4][2];    // vertices rotated into the plane
     double nl[4][2];    // side normals (-side_y, side_x) / NRM(side)
     double len[4];      // NRM(a1 - a0)
-    double xmax, ymin, ymax;   // bounding box of p2
-    double h;           // cull margin (see point_in_polygon)
+    double xmin, xmax, ymin, ymax;   // bounding box of p2
+    double h;           // cull margin (see ray_clearance)
+    double aa2d;        // 1.0 when p2 is an exactly axis-aligned rectangle
 };
 constexpr int kBlockerDoubles = sizeof(Blocker) / sizeof(double);
 
@@ -90,7 +91,8 @@ __device__ inline void make_blocker(const double *pts /*4x3*/, const double *n, 
         k.p2[i][1] = dot3(R + 3, pts + 3 * i);
     }
     double lmax = 0.0;
-    k.xmax = k.p2[0][0]; k.ymin = k.p2[0][1]; k.ymax = k.p2[0][1];
+    k.xmin = k.p2[0][0]; k.xmax = k.p2[0][0]; k.ymin = k.p2[0][1]; k.ymax = k.p2[0][1];
+    bool aa = true;
     for (int i = 0; i < 4; ++i) {
         const double *a1 = k.p2[(i + 1) % 4], *a0 = k.p2[i];
         const double side[2] = {a1[0] - a0[0], a1[1] - a0[1]};
@@ -99,35 +101,46 @@ __device__ inline void make_blocker(const double *pts /*4x3*/, const double *n, 
         k.nl[i][1] = side[0] / ns;
         k.len[i] = ns;
         lmax = fmax(lmax, ns);
+        // sides alternate exactly horizontal / exactly vertical, none degenerate
+        const bool horiz = side[1] == 0.0 && side[0] != 0.0;
+        const bool vert = side[0] == 0.0 && side[1] != 0.0;
+        aa = aa && ((i & 1) == 0 ? (horiz || vert) : true) && (horiz || vert);
+        k.xmin = fmin(k.xmin, a0[0]);
         k.xmax = fmax(k.xmax, a0[0]);
         k.ymin = fmin(k.ymin, a0[1]);
         k.ymax = fmax(k.ymax, a0[1]);
     }
+    // ... and form a proper rectangle: horizontal and vertical sides alternate, the two
+    // vertical sides span exactly [ymin, ymax], sit at xmin and xmax, and run in
+    // opposite directions
+    int n_vert = 0;
+    double dir_sum = 0.0;
+    for (int i = 0; i < 4 && aa; ++i) {
+        const double *a1 = k.p2[(i + 1) % 4], *a0 = k.p2[i], *a2 = k.p2[(i + 2) % 4];
+        const bool h0 = (a1[1] - a0[1]) == 0.0, h1 = (a2[1] - a1[1]) == 0.0;
+        if (h0 == h1) aa = false;
+        if (!h0) {
+            ++n_vert;
+            dir_sum += (a1[1] > a0[1]) ? 1.0 : -1.0;
+            aa = aa && fmin(a0[1], a1[1]) == k.ymin && fmax(a0[1], a1[1]) == k.ymax &&
+                 (a0[0] == k.xmin || a0[0] == k.xmax);
+        }
+    }
+    aa = aa && n_vert == 2 && dir_sum == 0.0 && k.xmin < k.xmax && k.ymin < k.ymax;
+    k.aa2d = aa ? 1.0 : 0.0;
     // A side only counts when the ray hit b satisfies
     // |b-a0| + |b-a1| - |a1-a0| <= 1e-6, i.e. b lies within sqrt(1e-6*L/2) of the
-    // side.  h = 0.01*max(1, L) puts 2h^2/L >= 2e-4 >> 1e-6 between the culled
-    // region and that band, far above any rounding error.
-    k.h = 0.01 * fmax(1.0, lmax);
+    // side.  h = sqrt(5e-6*L) puts 2h^2/L >= 1e-5 = 10 x the tolerance between the
+    // culled region and that band (the rounding error of the test is ~1e-15).
+    k.h = sqrt(5e-6 * fmax(lmax, 1e-3)) + 1e-9;
 }
 
-// geometry.py:614-686.  `culled` results are provably identical to the full
-// evaluation: b keeps the y of the query point and b_x > pt_x, so a query point
-// above/below the polygon's y-range or right of its x-range (by more than h)
-// cannot register a hit on any side -> count == 0 -> False.
-// point_in_polygon_2d is the part after the coplanarity test
-// |DOT(p - S0, n)| <= eta (geometry.py:641).
-__device__ inline bool point_in_polygon_2d(const double *p, const Blocker &k);
-
-__device__ inline bool point_in_polygon(const double *p, const Blocker &k) {
-    double d0[3];
-    sub3(p, k.s0, d0);
-    if (fabs(dot3(d0, k.n)) > kEta) return false;
-    return point_in_polygon_2d(p, k);
-}
-
-__device__ inline bool point_in_polygon_2d(const double *p, const Blocker &k) {
-    const double pt[2] = {dot3(k.r0, p), dot3(k.r1, p)};
-    if (pt[1] > k.ymax + k.h || pt[1] < k.ymin - k.h || pt[0] > k.xmax + k.h) return false;
+// geometry.py:658-686: winding count over the four sides for a query point that is
+// already rotated into the plane.  Out of line: it carries the x87 emulation and is
+// reached for a tiny fraction of the (pair, blocker) combinations only.
+__device__ __noinline__ bool point_in_polygon_sides(double ptx, double pty, const Blocker *kp) {
+    const Blocker &k = *kp;
+    const double pt[2] = {ptx, pty};
     int count = 0;
     const double pt1[2] = {pt[0] + 1., pt[1] + 0.};
     const double v[2] = {pt1[0] - pt[0], pt1[1] - pt[1]};
@@ -154,32 +167,89 @@ __device__ inline bool point_in_polygon_2d(const double *p, const Blocker &k) {
     return count != 0;
 }
 
+// How far a point q in the polygon's plane (2-D coordinates) is from the region where
+// the side loop of _point_in_polygon could return True.  For any s >= 0:
+//     ray_clearance(q) > s   ==>   point_in_polygon_sides(q') is False for every q'
+//                                  within distance s of q.
+// Two rules, both consequences of how the loop works (geometry.py:658-686):
+//  (ray)  the hit b of the +x ray keeps the y of the query point and has b_x > q_x,
+//         and a side only counts when b lies within sqrt(1e-6*L/2) << h of it: a
+//         point above/below the polygon's y-range or right of its x-range by more
+//         than h registers no side at all -> count == 0.
+//  (aa)   exactly axis-aligned rectangle, query point left of it and strictly inside
+//         its y-range: the horizontal sides give dp = v.nl = (+-0)*1 + 0*(+-1) = 0 (no
+//         hit); both vertical sides are hit in their interior, where
+//         |b-a0| + |b-a1| - |a1-a0| is pure rounding (~1e-15 << 1e-6), with
+//         d = (b_x - q_x) * nl_x of opposite signs (+1 and -1) -> count == 0.
+__device__ __forceinline__ double ray_clearance(double qx, double qy, const Blocker &k) {
+    const double c_ray = fmax(fmax(qy - k.ymax, k.ymin - qy), qx - k.xmax) - k.h;
+    const double c_aa = fmin(fmin(qy - k.ymin, k.ymax - qy), k.xmin - qx) - 1e-7;
+    return k.aa2d != 0.0 ? fmax(c_ray, c_aa) : c_ray;
+}
+constexpr double kClearGuard = 2e-9;   // absorbs the rounding of ray_clearance itself
+
+// geometry.py:645-686 for a point that passed the coplanarity test (:641)
+__device__ __forceinline__ bool point_in_polygon_2d(const double *p, const Blocker &k) {
+    const double ptx = dot3(k.r0, p), pty = dot3(k.r1, p);
+    if (ray_clearance(ptx, pty, k) > kClearGuard) return false;
+    return point_in_polygon_sides(ptx, pty, &k);
+}
+
+// geometry.py:614-686
+__device__ __forceinline__ bool point_in_polygon(const double *p, const Blocker &k) {
+    double d0[3];
+    sub3(p, k.s0, d0);
+    if (fabs(dot3(d0, k.n)) > kEta) return false;
+    return point_in_polygon_2d(p, k);
+}
+
 // geometry.py:841-909 evaluated for one blocking surface, organised so that the
-// common cases cost ~20 FP64 operations.  Only the ORDER of evaluation differs from
+// common cases cost ~25 FP64 operations.  Only the ORDER of evaluation differs from
 // the reference; the predicates are pure, so the value cannot:
 //  * inA / inB start with the coplanarity test (geometry.py:641), whose dot products
 //    dA, dB are needed anyway (dB is also the numerator of the plane hit parameter);
-//  * in the first branch (neither end point in the surface, :881-893) the reference
-//    requires  hit exists  AND  hit in polygon  AND  (hit-A).(hit-B) < 0.  The hit is
-//    B + fac*v (+ rounding ~1e-13) with fac = -(dB/dp), so (hit-A).(hit-B) =
-//    fac(1+fac)|v|^2 is positive whenever fac lies outside [-1, 0] by a margin; that
-//    margin test is done on products (no division) with thresholds 2e-3 / -1.002,
-//    which imply fac > 1e-3 resp. fac < -1.001 for the rounded quotient as well.
-//    v = B - A, cull_ok = |v|^2 > 1e-6.
+//  * first branch (neither end point in the surface, :881-893): the reference requires
+//    hit exists AND hit in polygon AND (hit-A).(hit-B) < 0, the hit being B + fac*v
+//    (+ rounding ~1e-13), fac = -(dB/dp).
+//    (a) (hit-A).(hit-B) = fac(1+fac)|v|^2 is positive whenever fac lies outside
+//        [-1, 0] by a margin; tested on products (no division) with thresholds
+//        2e-3 / -1.002, which imply fac > 1e-3 resp. fac < -1.001 for the rounded
+//        quotient as well.
+//    (b) an end point E in {A, B} that lies in the surface's plane (|dE| <= eta) but
+//        not in the polygon: in exact arithmetic dA = dB - dp, so the hit is
+//        E -+ (dE/dp) v, at most eta*|v|/|dp| away from E.  If ray_clearance(E)
+//        exceeds that distance (+3e-9 for rounding), "hit in polygon" is False.
+//    v = B - A, vlen = |v| (any rounding), cull_ok = |v|^2 > 1e-6.
 __device__ __forceinline__ bool blocked(const double *A, const double *B, const double *v,
-                                        bool cull_ok, const Blocker &k) {
+                                        double vlen, bool cull_ok, const Blocker &k) {
     double wa[3], w[3];
     sub3(A, k.s0, wa);
     sub3(B, k.s0, w);
     const double dA = dot3(wa, k.n);
     const double dB = dot3(w, k.n);
+    const bool copA = !(fabs(dA) > kEta), copB = !(fabs(dB) > kEta);
     bool inA = false, inB = false;
-    if (!(fabs(dA) > kEta)) inA = point_in_polygon_2d(A, k);
-    if (!(fabs(dB) > kEta)) inB = point_in_polygon_2d(B, k);
+    bool hit_misses = false;                    // rule (b)
+    const double dp = dot3(v, k.n);
+    if (copA | copB) {
+        const double slack = kEta * vlen / fabs(dp) + 3e-9;     // inf/nan when dp == 0: no cull
+        if (copA) {
+            const double ax = dot3(k.r0, A), ay = dot3(k.r1, A);
+            const double clr = ray_clearance(ax, ay, k);
+            if (!(clr > kClearGuard)) inA = point_in_polygon_sides(ax, ay, &k);
+            else if (!copB) hit_misses = clr > slack;
+        }
+        if (copB) {
+            const double bx = dot3(k.r0, B), by = dot3(k.r1, B);
+            const double clr = ray_clearance(bx, by, k);
+            if (!(clr > kClearGuard)) inB = point_in_polygon_sides(bx, by, &k);
+            else if (!copA) hit_misses = clr > slack;
+        }
+    }
     if (!inA && !inB) {
-        const double dp = dot3(v, k.n);
         if (!(fabs(dp) > 1e-6)) return false;               // geometry.py:599-604
         if (cull_ok) {
+            if (hit_misses) return false;
             const double u = -dB;
             const bool outside = dp > 0 ? (u > 2e-3 * dp || u < -1.002 * dp)
                                         : (u < 2e-3 * dp || u > -1.002 * dp);

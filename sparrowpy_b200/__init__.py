@@ -10,10 +10,10 @@ Drop-in surface of the reference package for this path::
 """
 __version__ = "0.1.0"
 
-from . import geometry, pyfar_shim, scenes, sound_object  # noqa: F401
+from . import brdf, geometry, pyfar_shim, scenes, sound_object  # noqa: F401
 from .geometry import Polygon  # noqa: F401
 from .radiosity import DirectionalRadiosityFast  # noqa: F401
 from . import testing  # noqa: F401
 
-__all__ = ["DirectionalRadiosityFast", "Polygon", "geometry", "sound_object",
+__all__ = ["DirectionalRadiosityFast", "Polygon", "geometry", "sound_object", "brdf",
            "scenes", "pyfar_shim", "testing"]

@@ -81,6 +81,22 @@ class Coordinates:
         return np.mod(np.arctan2(self._pts[..., 1], self._pts[..., 0]),
                       2 * np.pi)
 
+    @azimuth.setter
+    def azimuth(self, value):
+        r, col = self.radius, self.colatitude
+        az = np.broadcast_to(np.asarray(value, float), r.shape)
+        self._pts = np.stack([r * np.sin(col) * np.cos(az), r * np.sin(col) * np.sin(az),
+                              r * np.cos(col)], axis=-1)
+
+    def find_nearest(self, find):
+        """Index of the nearest point of ``self`` for every point of ``find``:
+        returns ``((index_array,), distance)`` like pyfar."""
+        a = self._pts.reshape(-1, 3)
+        b = find.cartesian.reshape(-1, 3)
+        d2 = np.sum((b[:, None, :] - a[None, :, :]) ** 2, axis=-1)
+        idx = np.argmin(d2, axis=1)
+        return (idx,), np.sqrt(d2[np.arange(len(b)), idx])
+
     def copy(self):
         out = Coordinates.from_cartesian(self._pts.copy())
         out.weights = None if self.weights is None else self.weights.copy()

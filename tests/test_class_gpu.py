@@ -127,3 +127,54 @@ def test_diffuse_tilde_equals_form_factors():
     np.testing.assert_allclose(tilde[iu], ff[iu], rtol=1e-12)
     area = rad.patches_area
     np.testing.assert_allclose(tilde.T[iu], (ff * area[:, None] / area[None, :])[iu], rtol=1e-12)
+
+
+def test_checkpoint_roundtrip_and_resume():
+    """to_dict / from_dict (reference RadiosityFast.py:841-886, tests/
+    test_DirectionalRadiosityFast.py:23-125): every array survives, and a resumed
+    object collects the same receiver ETC without re-running anything."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    g = load_golden("scene_directional")
+    rad = run_class(g)
+    rcv = pf.Coordinates.from_cartesian(g["receivers"])
+    mono = rad.collect_energy_receiver_mono(rcv).time
+    d = rad.to_dict()
+    assert set(d) >= {"walls_points", "visibility_matrix", "visible_patches", "form_factors",
+                      "form_factors_tilde", "patch_2_brdf_outgoing_index",
+                      "energy_exchange_etc", "energy_init_source", "speed_of_sound"}
+    assert isinstance(d["form_factors"], list) and isinstance(d["n_patches"], int)
+    rad2 = sp.DirectionalRadiosityFast.from_dict(d)
+    for name in ("_visibility_matrix", "_visible_patches", "_form_factors",
+                 "_form_factors_tilde", "_patch_2_brdf_outgoing_index",
+                 "_energy_init_source", "_distance_patches_to_source",
+                 "_energy_exchange_etc"):
+        np.testing.assert_array_equal(np.asarray(getattr(rad2, name)),
+                                      np.asarray(getattr(rad, name)), err_msg=name)
+    assert rad2.speed_of_sound == rad.speed_of_sound
+    mono2 = rad2.collect_energy_receiver_mono(rcv).time
+    assert rel_err(mono2, mono) < 1e-12
+    # an untouched object serialises its missing stages as the string 'None'
+    fresh = sp.DirectionalRadiosityFast.from_polygon(sp.testing.shoebox_room_stub(1, 1, 1), 1.0)
+    assert fresh.to_dict()["form_factors"] == "None"
+    again = sp.DirectionalRadiosityFast.from_dict(fresh.to_dict())
+    assert again.n_patches == fresh.n_patches and again._form_factors is None
+
+
+def test_direct_sound_added_at_floor_delay():
+    """collect_energy_receiver_mono(direct_sound=True) (RadiosityFast.py:594-657)."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    rad = sp.DirectionalRadiosityFast.from_polygon(sp.testing.shoebox_room_stub(3, 3, 3), 1.0)
+    rad.bake_geometry()
+    src, rcv = np.array([1.0, 1.0, 1.0]), np.array([[2.0, 2.2, 1.4]])
+    rad.init_source_energy(pf.Coordinates(*src))
+    rad.calculate_energy_exchange(343.2, 1e-3, 0.05, max_reflection_order=2)
+    r = pf.Coordinates.from_cartesian(rcv)
+    a = rad.collect_energy_receiver_mono(r, direct_sound=False).time
+    b = rad.collect_energy_receiver_mono(r, direct_sound=True).time
+    dist = np.linalg.norm(rcv[0] - src)
+    k = int(dist / 343.2 / 1e-3)
+    diff = b - a
+    assert np.count_nonzero(diff) == 1
+    np.testing.assert_allclose(diff[0, 0, k], 1 / (4 * np.pi * dist ** 2), rtol=1e-12)

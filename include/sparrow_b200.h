@@ -79,6 +79,17 @@ int spb_exchange_init(void *e_total, void *e_prev, const void *e0,
                       int64_t n_dirs, int64_t n_bands, int64_t n_samples, int64_t ld,
                       int64_t pad, int dtype, void *stream);
 
+/* The scatter step of spb_exchange_init alone, into the band window
+ * [band_lo, band_lo + n_bands_src) of buffers that hold n_bands_total bands and were
+ * zeroed by the caller.  Used to batch several sources: source s occupies the bands
+ * [s*B, (s+1)*B) -- sources are just more independent channels of the exchange.
+ * e0: [N, D, n_bands_src]. */
+int spb_exchange_scatter(void *e_total, void *e_prev, const void *e0,
+                         const int32_t *delay0, int64_t n_patches, int64_t n_alloc,
+                         int64_t n_dirs, int64_t n_bands_src, int64_t band_lo,
+                         int64_t n_bands_total, int64_t n_samples, int64_t ld,
+                         int64_t pad, int dtype, void *stream);
+
 /* Stage 1 of one order for receiver patches [j_lo, j_hi) and bands [b_lo, b_hi)
  * (everything on one GPU; a receiver shard, or one band of a pipelined schedule, on
  * several).  g: [B, C*N, LD], only rows of non-empty segments in the range are

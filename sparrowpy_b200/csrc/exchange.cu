@@ -26,7 +26,7 @@ __global__ void k_init_scatter(T *__restrict__ e_total, T *__restrict__ e_prev,
                                const T *__restrict__ e0,
                                const int32_t *__restrict__ delay0, int64_t n_patches,
                                int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
-                               int64_t n_samples, int64_t ld, int64_t pad) {
+                               int64_t band_lo, int64_t n_samples, int64_t ld, int64_t pad) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_patches * n_dirs * n_bands) return;
     const int64_t b = idx % n_bands;
@@ -35,7 +35,7 @@ __global__ void k_init_scatter(T *__restrict__ e_total, T *__restrict__ e_prev,
     const int32_t d = delay0[patch];
     if (d < 0 || d >= n_samples) return;   // out-of-range energy is dropped
     const T v = e0[idx];
-    const int64_t row = b * n_alloc * n_dirs + pd;
+    const int64_t row = (band_lo + b) * n_alloc * n_dirs + pd;
     e_total[row * ld + pad + d] += v;
     if (e_prev) e_prev[row * ld + pad + d] += v;
 }
@@ -244,18 +244,26 @@ k_collect_patchwise(const T *__restrict__ e_total, const int32_t *__restrict__ r
 // typed launchers
 // ---------------------------------------------------------------------------
 template <typename T>
+int scatter_t(void *e_total, void *e_prev, const void *e0, const int32_t *delay0,
+              int64_t n_patches, int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
+              int64_t band_lo, int64_t n_samples, int64_t ld, int64_t pad, cudaStream_t st) {
+    const int64_t n_in = n_patches * n_dirs * n_bands;
+    if (n_in == 0) return 0;
+    k_init_scatter<T><<<(unsigned)ceil_div(n_in, 256), 256, 0, st>>>(
+        (T *)e_total, (T *)e_prev, (const T *)e0, delay0, n_patches, n_alloc, n_dirs, n_bands,
+        band_lo, n_samples, ld, pad);
+    return check_launch("k_init_scatter");
+}
+
+template <typename T>
 int init_t(void *e_total, void *e_prev, const void *e0, const int32_t *delay0,
            int64_t n_patches, int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
            int64_t n_samples, int64_t ld, int64_t pad, cudaStream_t st) {
     const int64_t n_rows = n_alloc * n_dirs * n_bands;
     SPB_CUDA(cudaMemsetAsync(e_total, 0, sizeof(T) * n_rows * ld, st));
     if (e_prev) SPB_CUDA(cudaMemsetAsync(e_prev, 0, sizeof(T) * n_rows * ld, st));
-    const int64_t n_in = n_patches * n_dirs * n_bands;
-    if (n_in == 0) return 0;
-    k_init_scatter<T><<<(unsigned)ceil_div(n_in, 256), 256, 0, st>>>(
-        (T *)e_total, (T *)e_prev, (const T *)e0, delay0, n_patches, n_alloc, n_dirs, n_bands,
-        n_samples, ld, pad);
-    return check_launch("k_init_scatter");
+    return scatter_t<T>(e_total, e_prev, e0, delay0, n_patches, n_alloc, n_dirs, n_bands, 0,
+                        n_samples, ld, pad, st);
 }
 
 template <typename T>
@@ -358,6 +366,24 @@ int spb_exchange_init(void *e_total, void *e_prev, const void *e0, const int32_t
     if (dtype == SPB_F32)
         return init_t<float>(e_total, e_prev, e0, delay0, n_patches, n_alloc, n_dirs, n_bands,
                              n_samples, ld, pad, st);
+    return fail(-1, "invalid argument", "dtype");
+}
+
+int spb_exchange_scatter(void *e_total, void *e_prev, const void *e0, const int32_t *delay0,
+                         int64_t n_patches, int64_t n_alloc, int64_t n_dirs,
+                         int64_t n_bands_src, int64_t band_lo, int64_t n_bands_total,
+                         int64_t n_samples, int64_t ld, int64_t pad, int dtype, void *stream) {
+    SPB_REQUIRE(e_total && e0 && delay0, "null pointer");
+    SPB_REQUIRE(ld >= pad + n_samples, "ld < pad + n_samples");
+    SPB_REQUIRE(n_alloc >= n_patches, "n_alloc < n_patches");
+    SPB_REQUIRE(band_lo >= 0 && band_lo + n_bands_src <= n_bands_total, "band window");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SPB_F64)
+        return scatter_t<double>(e_total, e_prev, e0, delay0, n_patches, n_alloc, n_dirs,
+                                 n_bands_src, band_lo, n_samples, ld, pad, st);
+    if (dtype == SPB_F32)
+        return scatter_t<float>(e_total, e_prev, e0, delay0, n_patches, n_alloc, n_dirs,
+                                n_bands_src, band_lo, n_samples, ld, pad, st);
     return fail(-1, "invalid argument", "dtype");
 }
 

@@ -57,7 +57,7 @@ class ShardedExchange:
     """
 
     def __init__(self, tables, n_samples, device, group=None, compute=None,
-                 layout=None):
+                 layout=None, need_orders=True):
         self.t = tables
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -100,11 +100,13 @@ class ShardedExchange:
                 print(f"[sparrowpy_b200] symmetric memory unavailable ({exc}); "
                       "using NCCL all-gather", flush=True)
                 self.comm, self.handles = "nccl", None
-        if self.handles is None:
+        if self.handles is None and need_orders:
             self.e_a = torch.zeros((rows, self.ld), dtype=tdt, device=device)
             self.e_b = torch.zeros((rows, self.ld), dtype=tdt, device=device)
+        elif self.handles is None:
+            self.e_a = self.e_b = None           # order 0 only: no ping-pong buffers
         self.e_total = torch.zeros((rows, self.ld), dtype=tdt, device=device)
-        g_rows = t.n_bands * t.n_classes * t.n_patches
+        g_rows = t.n_bands * t.n_classes * t.n_patches if need_orders else 1
         self.g = torch.empty((max(g_rows, 1), self.ld), dtype=tdt, device=device)
         self.compute = compute or self._cuda_order
         self.comm_stream = torch.cuda.Stream(device=device) if (
@@ -169,27 +171,42 @@ class ShardedExchange:
     # -- driver --------------------------------------------------------------
     def init(self, e0, delay0):
         """Initial energy (order 0): replicated into e_a (every rank needs all
-        senders), own shard only into e_total."""
+        senders), own shard only into e_total.
+
+        e0 (N, D, B) with delay0 (N,), or a batch of sources e0 (S, N, D, B) with
+        delay0 (S, N) when the tables were tiled for S sources."""
         t = self.t
-        self.e_b.zero_()
-        e0, delay0 = t.to_internal(e0), t.to_internal(delay0)
+        if self.e_b is not None:
+            self.e_b.zero_()
+        if e0.dim() == 3:
+            e0, delay0 = e0[None], delay0[None]
+        n_src = e0.shape[0]
+        nb_src = t.n_bands // n_src
         if self.cuda:
             tdt = _lib.torch_dtype(t.dtype)
-            _lib.call("spb_exchange_init", self.e_total, self.e_a, e0.to(tdt).contiguous(),
-                      delay0.to(torch.int32).contiguous(), t.n_patches, self.n_alloc,
-                      t.n_dirs, t.n_bands, self.n_samples, self.ld, self.pad,
-                      _lib.I32(t.dtype), _lib.stream_ptr())
+            self.e_total.zero_()
+            if self.e_a is not None:
+                self.e_a.zero_()
+            for s in range(n_src):
+                _lib.call("spb_exchange_scatter", self.e_total, self.e_a,
+                          t.to_internal(e0[s]).to(tdt).contiguous(),
+                          t.to_internal(delay0[s]).to(torch.int32).contiguous(),
+                          t.n_patches, self.n_alloc, t.n_dirs, nb_src, s * nb_src, t.n_bands,
+                          self.n_samples, self.ld, self.pad, _lib.I32(t.dtype),
+                          _lib.stream_ptr())
         else:  # CPU path of the gloo tests
             self.e_total.zero_()
             self.e_a.zero_()
-            n, d, nb = e0.shape
-            for b in range(nb):
-                for i in range(n):
-                    dl = int(delay0[i])
-                    if dl < self.n_samples:
-                        r0 = (b * self.n_alloc + i) * d
-                        self.e_total[r0:r0 + d, self.pad + dl] += e0[i, :, b].to(
-                            self.e_total.dtype)
+            for s in range(n_src):
+                e0s, d0s = t.to_internal(e0[s]), t.to_internal(delay0[s])
+                n, d, nb = e0s.shape
+                for b in range(nb):
+                    for i in range(n):
+                        dl = int(d0s[i])
+                        if dl < self.n_samples:
+                            r0 = ((s * nb_src + b) * self.n_alloc + i) * d
+                            self.e_total[r0:r0 + d, self.pad + dl] += e0s[i, :, b].to(
+                                self.e_total.dtype)
             self.e_a.copy_(self.e_total)
         if self.world > 1:
             keep = [self.shard_rows(self.e_total, b).clone() for b in range(t.n_bands)]

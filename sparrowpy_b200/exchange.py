@@ -36,6 +36,17 @@ class PairTables:
     rank: torch.Tensor = None      # (n_user,) int64 caller's patch id -> internal index
     n_user: int = 0                # caller's patch count (n_patches is the internal one)
 
+    def tiled(self, n_sources):
+        """Tables for a batch of ``n_sources`` sources: a source is one more group of
+        independent channels, so source s simply occupies the bands [s*B, (s+1)*B)
+        (same pair structure, BRDF coefficients repeated)."""
+        import dataclasses
+        if n_sources == 1:
+            return self
+        return dataclasses.replace(
+            self, coef=self.coef.repeat(1, 1, n_sources).contiguous(),
+            n_bands=self.n_bands * n_sources)
+
     def to_internal(self, per_patch, dim=0):
         """Reorder a per-patch tensor (patch axis ``dim``) into the internal patch
         numbering; holes of the internal numbering are zero."""
@@ -184,12 +195,13 @@ class EnergyHistogram:
     patch index of the pair tables (``tables.rank`` maps the caller's ids to it)."""
 
     def __init__(self, data, n_patches, n_dirs, n_bands, n_samples, pad, n_alloc=None,
-                 tables=None):
+                 tables=None, n_sources=None):
         self.data = data                    # (B * n_alloc * D, LD)
         self.n_patches, self.n_dirs = n_patches, n_dirs      # internal patch count
         self.n_bands, self.n_samples, self.pad = n_bands, n_samples, pad
         self.n_alloc = n_patches if n_alloc is None else n_alloc
         self.tables = tables
+        self.n_sources = n_sources          # None: single source; else bands = S * B
 
     @property
     def ld(self):
@@ -206,7 +218,11 @@ class EnergyHistogram:
         v = v[:, :self.n_patches, :, self.pad:self.pad + self.n_samples]
         if self.rank is not None:
             v = v.index_select(1, self.rank)
-        return v.permute(1, 2, 0, 3)
+        v = v.permute(1, 2, 0, 3)
+        if self.n_sources is not None:      # (S, N, D, B, T)
+            n, d, sb, t = v.shape
+            v = v.reshape(n, d, self.n_sources, sb // self.n_sources, t).permute(2, 0, 1, 3, 4)
+        return v
 
     def to_internal(self, per_patch, dim):
         return per_patch if self.tables is None else self.tables.to_internal(per_patch, dim)
@@ -239,6 +255,8 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
     e0: (N, D, B) device tensor; delay0: (N,) int32 source->patch delay bins.
     Returns an :class:`EnergyHistogram` holding sum_{k<=K} E_k.
     """
+    if e0.dim() == 4:
+        return _energy_exchange_batch(tables, e0, delay0, n_samples, max_order)
     t = tables
     tdt = _lib.torch_dtype(t.dtype)
     device = e0.device
@@ -256,6 +274,20 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
                            tables=t)
 
 
+def _energy_exchange_batch(tables, e0, delay0, n_samples, max_order):
+    """Several sources at once: e0 (S, N, D, B), delay0 (S, N).  The sources ride along
+    as extra bands (PairTables.tiled), so every kernel launch covers all of them.
+    Returns an EnergyHistogram whose dense() is (S, N, D, B, T)."""
+    from .distributed import ShardedExchange
+    n_src = e0.shape[0]
+    sx = ShardedExchange(tables.tiled(n_src), n_samples, e0.device,
+                         need_orders=max_order >= 1)
+    sx.init(e0, delay0)
+    hist = sx.run(max(0, int(max_order)))
+    hist.n_sources = n_src
+    return hist
+
+
 def collect_mono(hist, rdir, shift, scale, n_split=None):
     """Sum of all patch histograms at each receiver, (R, B, T)
     (``collect_energy_receiver_mono``, RadiosityFast.py:570-602 / :1148-1185).
@@ -266,6 +298,8 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
     tdt = hist.data.dtype
     code = _lib.dtype_code(tdt)
     rdir, shift, scale = (hist.to_internal(x, 1) for x in (rdir, shift, scale))
+    if hist.n_sources is not None:          # the same receiver factors for every source
+        scale = scale.repeat(1, 1, hist.n_sources)
     if n_split is None:
         n_split = max(1, min(64, hist.n_patches // 256))
     out = torch.empty((n_rcv, hist.n_bands, hist.n_samples), dtype=tdt,
@@ -282,6 +316,8 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
                   hist.ld,
                   hist.pad, out[r0:r1], partial, n_split, _lib.I32(code),
                   _lib.stream_ptr())
+    if hist.n_sources is not None:          # (S, R, B, T)
+        out = out.reshape(n_rcv, hist.n_sources, -1, hist.n_samples).permute(1, 0, 2, 3)
     return out
 
 

@@ -272,7 +272,34 @@ class DirectionalRadiosityFast:
             raise ValueError(
                 "source must be pf.Coordinates or sparrowpy SoundSource")
         self._source = source
+        if getattr(source, "directivity", None) is not None:
+            raise NotImplementedError(
+                "source directivities (DirectivityMS / SOFA) are outside the B200 "
+                "hot path; see DESIGN.md")
+        svis, d0, e0 = self._source_energy(source_position[None])
+        self._source_vis_dev, self._d0_dev, self._e0_dev = svis[0], d0[0], e0[0]
+        self._host["energy_init_source"] = None
+        self._host["distance_patches_to_source"] = None
 
+    def init_source_energy_batch(self, sources):
+        """Extension: several source positions at once.
+
+        ``sources``: Coordinates of cshape (S,).  The following
+        ``calculate_energy_exchange`` propagates all S sources in the same kernel
+        launches (a source is one more group of independent channels) and
+        ``collect_energy_receiver_mono`` returns TimeData of cshape (S, R, n_bins).
+        """
+        if not isinstance(sources, _COORD_TYPES) or sources.cdim != 1:
+            raise ValueError("sources must be pf.Coordinates of shape (n_sources, 3)")
+        self._source = sources
+        positions = np.asarray(sources.cartesian, float).reshape(-1, 3)
+        self._source_vis_dev, self._d0_dev, self._e0_dev = self._source_energy(positions)
+        self._host["energy_init_source"] = None
+        self._host["distance_patches_to_source"] = None
+
+    def _source_energy(self, positions):
+        """Point visibility, source->patch energy and distances for S positions:
+        (vis (S,N) bool, d0 (S,N), e0 (S,N,D,B)) on the device."""
         if self._brdf_incoming_directions is None:
             frequencies = np.array([0]) if self._frequencies is None else \
                 self._frequencies
@@ -288,25 +315,22 @@ class DirectionalRadiosityFast:
                 _FrequencyData(np.zeros_like(frequencies, dtype=float), frequencies))
             self._frequencies = frequencies
 
-        if getattr(source, "directivity", None) is not None:
-            raise NotImplementedError(
-                "source directivities (DirectivityMS / SOFA) are outside the B200 "
-                "hot path; see DESIGN.md")
-
         g = self._geom()
         dev = self._device
         vi, vo, brdf, bidx = self._brdf_tables()
-        src = torch.from_numpy(source_position.copy()).to(dev)
-        svis = bake.visibility_pt2p(src, g["center"], g["walls_normal"],
-                                    g["walls_points"])[0]
+        src = torch.from_numpy(np.ascontiguousarray(positions, dtype=float)).to(dev)
+        svis = bake.visibility_pt2p(src, g["center"], g["walls_normal"], g["walls_points"])
         air = torch.from_numpy(np.real(self._air_attenuation).astype(float)).to(dev)
-        d0, e0, _ = bake.source_energy(
-            src, g["center"], g["points"], svis, air, g["wall_ids"],
-            torch.from_numpy(vi).to(dev), torch.from_numpy(brdf).to(dev),
-            torch.from_numpy(bidx).to(dev), vo.shape[1])
-        self._source_vis_dev, self._d0_dev, self._e0_dev = svis, d0, e0
-        self._host["energy_init_source"] = None
-        self._host["distance_patches_to_source"] = None
+        vi_d, brdf_d = torch.from_numpy(vi).to(dev), torch.from_numpy(brdf).to(dev)
+        bidx_d = torch.from_numpy(bidx).to(dev)
+        d0s, e0s = [], []
+        for s in range(src.shape[0]):
+            d0, e0, _ = bake.source_energy(
+                src[s], g["center"], g["points"], svis[s], air, g["wall_ids"], vi_d, brdf_d,
+                bidx_d, vo.shape[1])
+            d0s.append(d0)
+            e0s.append(e0)
+        return svis, torch.stack(d0s), torch.stack(e0s)
 
     # ------------------------------------------------------------------
     # exchange: RadiosityFast.py:524-568
@@ -340,7 +364,7 @@ class DirectionalRadiosityFast:
             delay0 = bake.delay_bins(self._d0_dev, speed_of_sound, etc_time_resolution)
             if max_reflection_order < 1:
                 # initial energy only (RadiosityFast.py:550-555): no pair tables needed
-                n, n_out, n_bins = self._e0_dev.shape
+                n, n_out, n_bins = self._e0_dev.shape[-3:]
                 empty = torch.zeros(0, dtype=torch.int64, device=self._device)
                 tables = exchange.build_pair_tables(
                     empty, empty, torch.zeros(0, dtype=torch.float64, device=self._device),
@@ -352,11 +376,11 @@ class DirectionalRadiosityFast:
                     raise _lib.SparrowB200Error(
                         "bake_geometry must be called before calculate_energy_exchange")
                 tables = self._pair_tables(speed_of_sound, etc_time_resolution, n_samples)
-                if (tables.n_dirs, tables.n_bands) != tuple(self._e0_dev.shape[1:]):
+                if (tables.n_dirs, tables.n_bands) != tuple(self._e0_dev.shape[-2:]):
                     raise ValueError(
                         "BRDF / frequency layout changed after bake_geometry: "
                         f"baked (n_directions, n_bins)={(tables.n_dirs, tables.n_bands)}, "
-                        f"source energy has {tuple(self._e0_dev.shape[1:])}; "
+                        f"source energy has {tuple(self._e0_dev.shape[-2:])}; "
                         "set the BRDF before bake_geometry")
             self._hist = exchange.energy_exchange(
                 tables, self._e0_dev, delay0, n_samples, max_reflection_order)
@@ -409,6 +433,8 @@ class DirectionalRadiosityFast:
         etc_data = _np(mono.double())
         times = np.arange(etc_data.shape[-1]) * self._etc_time_resolution
         etc = _TimeData(etc_data, times)
+        if direct_sound and hist.n_sources is not None:
+            raise NotImplementedError("direct sound with a batch of sources")
         if direct_sound:
             direct, n_sample_delay = self.calculate_direct_sound(receivers)
             i_receivers = np.arange(len(n_sample_delay))

@@ -94,7 +94,7 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
              const int64_t *__restrict__ ent_ptr, const TileRecord<T> *__restrict__ recs,
              int64_t n_patches, int64_t n_alloc, int64_t n_blocks, int64_t n_dirs,
              int64_t b_lo, int64_t jb_lo, int64_t n_jb, int64_t n_classes, int64_t t_pad,
-             int64_t ld, int64_t pad) {
+             int64_t ld, int64_t pad, int warps_t) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Stage<T> *stages = reinterpret_cast<Stage<T> *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(Stage<T>) * kStages);
@@ -110,8 +110,10 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
     const int64_t tile = c * n_blocks + jb;
     const int64_t e0 = ent_ptr[tile], e1 = ent_ptr[tile + 1];
     if (e0 == e1) return;                         // no pairs: rows are never read
-    const int64_t t0 = (int64_t)blockIdx.y * kCtaT;
-    const int n_active = (int)min((int64_t)kWarpsT, (t_pad - t0) / kSliceT);
+    // warps_t (<= 8) time slices per CTA: small problems use fewer slices per CTA and
+    // more CTAs along time to fill the machine
+    const int64_t t0 = (int64_t)blockIdx.y * warps_t * kSliceT;
+    const int n_active = (int)min((int64_t)warps_t, (t_pad - t0) / kSliceT);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -221,10 +223,15 @@ int gather_tiled_t(const void *e_prev, void *g, const int64_t *ent_ptr, const vo
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((unsigned)n_cta, (unsigned)ceil_div(t_pad, kCtaT));
+    // 2 CTAs fit per SM; aim for at least ~2 waves on 148 SMs before giving every CTA
+    // the full 1024-bin window
+    int warps_t = kWarpsT;
+    while (warps_t > 2 && n_cta * ceil_div(t_pad, (int64_t)warps_t * kSliceT) < 2 * 296)
+        warps_t /= 2;
+    dim3 grid((unsigned)n_cta, (unsigned)ceil_div(t_pad, (int64_t)warps_t * kSliceT));
     k_gather_tma<T><<<grid, (kWarpsT + 1) * 32, smem, st>>>(
         (const T *)e_prev, (T *)g, ent_ptr, (const TileRecord<T> *)recs, n_patches, n_alloc,
-        n_blocks, n_dirs, b_lo, jb_lo, n_jb, n_classes, t_pad, ld, pad);
+        n_blocks, n_dirs, b_lo, jb_lo, n_jb, n_classes, t_pad, ld, pad, warps_t);
     return check_launch("k_gather_tma");
 }
 

@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default=os.environ.get("SPB_BENCH_CONFIG", "c2"),
+    ap.add_argument("--config", default=os.environ.get("SPB_BENCH_CONFIG", "c4"),
                     choices=sorted(CONFIGS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--gather", default=os.environ.get("SPB_GATHER", "tma"),
@@ -273,7 +273,7 @@ def main():
     log(f"baked {args.config}: N={rad.n_patches} P={rad._baked['pairs'].shape[0]} "
         f"in {time.time() - t0:.1f}s")
     n_samples, orders = cfg["n_samples"], cfg["orders"]
-    tables = rad._pair_tables(SPEED_OF_SOUND, DT, n_samples)
+    tables = rad._pair_tables(SPEED_OF_SOUND, DT, n_samples, n_shards=world)
     n_pairs = int(rad._baked["pairs"].shape[0])
     bake_info = time_bake(rad, n_pairs) if rank == 0 else None
     n_dir, n_band = tables.n_dirs, tables.n_bands
@@ -348,7 +348,9 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
-    share = (sx.j_hi - sx.j_lo) / max(rad.n_patches, 1)
+    # this rank's share of the directed pairs (shards are balanced by dealing the
+    # receiver tiles round-robin, so the patch share is the pair share up to noise)
+    share = 1.0 / world
     # algorithmic bytes per pair.bin exchange = B*(1+2D)*sizeof; one gather
     # launch processes this rank's directed pairs x T bins of one order
     alg_bytes_launch = (2.0 * n_pairs * share * n_samples * n_band * (1 + 2 * n_dir) * esize

@@ -139,7 +139,7 @@ def calculate_area(points):
     return area
 
 
-def compact_patch_order(patches_points, patch_to_wall_ids, block=(2, 4)):
+def compact_patch_order(patches_points, patch_to_wall_ids, block=(2, 4), n_shards=1):
     """Internal patch numbering in which every run of 8 consecutive indices is a
     compact ``block`` (2 x 4 patches) of one wall instead of an 8 x 1 strip.
 
@@ -147,6 +147,10 @@ def compact_patch_order(patches_points, patch_to_wall_ids, block=(2, 4)):
     numbering gives the same result).  Blocks at the rim of a wall grid are not full,
     so the internal index space has holes: returns ``(rank, n_internal)`` with
     ``rank[patch] = internal index`` and ``n_internal = 8 * number of blocks >= N``.
+
+    ``n_shards`` > 1 deals the blocks round-robin to that many equal contiguous index
+    ranges (the receiver shards of a multi-GPU run), so that every shard gets the
+    same mix of walls and therefore a similar number of visible pairs.
     """
     pts = np.asarray(patches_points, dtype=float)
     ids = np.asarray(patch_to_wall_ids)
@@ -169,5 +173,12 @@ def compact_patch_order(patches_points, patch_to_wall_ids, block=(2, 4)):
         within = (idx[0] % block[0]) * block[1] + idx[1] % block[1]
         rank[sel] = base + blk * per + within
         base += (int(blk.max()) + 1) * per
+    n_internal = int(base)
+    if n_shards > 1:
+        n_tiles = n_internal // per
+        per_shard = -(-n_tiles // n_shards)
+        tile = rank // per
+        rank = ((tile % n_shards) * per_shard + tile // n_shards) * per + rank % per
+        n_internal = n_shards * per_shard * per
     assert len(np.unique(rank)) == len(rank)
-    return rank, int(base)
+    return rank, n_internal

@@ -335,14 +335,16 @@ class DirectionalRadiosityFast:
     # ------------------------------------------------------------------
     # exchange: RadiosityFast.py:524-568
     # ------------------------------------------------------------------
-    def _pair_tables(self, speed_of_sound, dt, n_samples):
-        key = (float(speed_of_sound), float(dt), int(n_samples), self._dtype)
+    def _pair_tables(self, speed_of_sound, dt, n_samples, n_shards=1):
+        """Exchange tables for (c, dt, T); ``n_shards`` > 1 numbers the patches so that
+        equal contiguous receiver shards are load-balanced (multi-GPU runs)."""
+        key = (float(speed_of_sound), float(dt), int(n_samples), self._dtype, int(n_shards))
         if self._tables is None or self._tables[0] != key:
             b = self._baked
             delay = bake.delay_bins(b["dist"], speed_of_sound, dt).long()
             delay = torch.stack([delay, delay], dim=1).reshape(-1)
             rank, n_internal = geometry.compact_patch_order(
-                self._patches_points, self._patch_to_wall_ids)
+                self._patches_points, self._patch_to_wall_ids, n_shards=n_shards)
             tables = exchange.build_pair_tables(
                 b["sender"], b["receiver"], b["ff_dir"], delay, b["out_dir"], b["cls"],
                 b["coef"], self.n_patches, n_samples, self._dtype,

@@ -24,9 +24,19 @@ ok = True
 for dtype in ("f64", "f32"):
     rad = bench.build_scene(cfg, dtype)
     n_samples = cfg["n_samples"]
-    tables = rad._pair_tables(bench.SPEED_OF_SOUND, bench.DT, n_samples)
+    world = dist.get_world_size()
     delay0 = bake.delay_bins(rad._d0_dev, bench.SPEED_OF_SOUND, bench.DT)
+    # single-GPU reference with the default patch numbering ...
+    tables1 = rad._pair_tables(bench.SPEED_OF_SOUND, bench.DT, n_samples)
+    ref1 = exchange.energy_exchange(tables1, rad._e0_dev, delay0, n_samples, orders).dense().clone()
+    # ... and with the shard-balanced numbering the multi-GPU run uses (same tiles, so
+    # the sharded result must be bit-identical to this one)
+    tables = rad._pair_tables(bench.SPEED_OF_SOUND, bench.DT, n_samples, n_shards=world)
     ref = exchange.energy_exchange(tables, rad._e0_dev, delay0, n_samples, orders).dense().clone()
+    renum = float((ref - ref1).abs().max() / ref1.abs().max())
+    ok &= renum < (1e-12 if dtype == "f64" else 1e-5)
+    if rank == 0:
+        print(f"{dtype} renumbering for {world} shards: max rel diff {renum:.2e}", flush=True)
     for mode in ("multicast", "p2p", "nccl"):
         os.environ["SPB_COMM"] = mode
         sx = distributed.ShardedExchange(tables, n_samples, dev)

@@ -295,7 +295,7 @@ def main():
         ev0.record(cst)
         if args.gather == "tma":
             _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
-                      t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
+                      sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
                       sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32, sp)
         else:
             _lib.call("spb_exchange_gather", prev, sx.g, t.seg_ptr, t.src, t.wgt, t.dly,

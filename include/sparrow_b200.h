@@ -110,11 +110,14 @@ int spb_exchange_gather(const void *e_prev, void *g, const int64_t *seg_ptr,
  * = weights and (delay - dmin) of the R receivers for sender row src; dmin (low 24
  * bits, a multiple of the bucket) and a reload mask (high 8 bits: slot s starts a
  * new shift; empty slots have w = 0 and repeat the previous shift).  j_lo must be a
- * multiple of R. */
+ * multiple of R.  cta_order (optional, may be 0): a permutation of the
+ * n_classes * ceil((j_hi - j_lo)/R) local tiles (index = class * n_tile_cols + tile
+ * column) giving the launch order, e.g. longest record lists first. */
 int spb_tile_geometry(int dtype, int64_t *receivers_per_tile, int64_t *delay_bucket,
                       int64_t *record_bytes);
 int spb_exchange_gather_tiled(const void *e_prev, void *g, const int64_t *ent_ptr,
-                              const void *recs, int64_t n_patches, int64_t n_alloc,
+                              const void *recs, const int32_t *cta_order,
+                              int64_t n_patches, int64_t n_alloc,
                               int64_t n_classes, int64_t n_dirs, int64_t n_bands,
                               int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi,
                               int64_t t_pad, int64_t ld, int64_t pad, int dtype,

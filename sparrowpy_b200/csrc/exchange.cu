@@ -473,7 +473,7 @@ int spb_energy_exchange(const void *e0, const int32_t *delay0, const int64_t *se
     void *prev = e_a, *cur = e_b;
     for (int64_t k = 0; k < max_order; ++k) {
         if (recs)
-            rc = spb_exchange_gather_tiled(prev, g, ent_ptr, recs, n, n, n_classes, n_dirs,
+            rc = spb_exchange_gather_tiled(prev, g, ent_ptr, recs, nullptr, n, n, n_classes, n_dirs,
                                            n_bands, 0, n_bands, 0, n, t_pad, ld, pad, dtype,
                                            stream);
         else

@@ -94,7 +94,7 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
              const int64_t *__restrict__ ent_ptr, const TileRecord<T> *__restrict__ recs,
              int64_t n_patches, int64_t n_alloc, int64_t n_blocks, int64_t n_dirs,
              int64_t b_lo, int64_t jb_lo, int64_t n_jb, int64_t n_classes, int64_t t_pad,
-             int64_t ld, int64_t pad, int warps_t) {
+             int64_t ld, int64_t pad, int warps_t, const int32_t *__restrict__ cta_order) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Stage<T> *stages = reinterpret_cast<Stage<T> *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(Stage<T>) * kStages);
@@ -104,7 +104,10 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
     const int warp = threadIdx.x >> 5;
     const int64_t n_local = n_classes * n_jb;
     const int64_t b = b_lo + blockIdx.x / n_local;
-    const int64_t loc = blockIdx.x % n_local;
+    // cta_order: launch position -> local tile, longest record lists first, so that the
+    // short tiles fill the tail of the grid (the hardware hands out CTAs in index order)
+    const int64_t pos = blockIdx.x % n_local;
+    const int64_t loc = cta_order ? cta_order[pos] : pos;
     const int64_t c = loc / n_jb;
     const int64_t jb = jb_lo + (loc - c * n_jb);
     const int64_t tile = c * n_blocks + jb;
@@ -207,9 +210,9 @@ k_gather_tma(const T *__restrict__ e_prev, T *__restrict__ g,
 
 template <typename T>
 int gather_tiled_t(const void *e_prev, void *g, const int64_t *ent_ptr, const void *recs,
-                   int64_t n_patches, int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
-                   int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi, int64_t t_pad,
-                   int64_t ld, int64_t pad, cudaStream_t st) {
+                   const int32_t *cta_order, int64_t n_patches, int64_t n_alloc,
+                   int64_t n_classes, int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+                   int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, cudaStream_t st) {
     const int64_t n_blocks = ceil_div(n_patches, kR);
     const int64_t jb_lo = j_lo / kR, jb_hi = ceil_div(j_hi, kR);
     const int64_t n_jb = jb_hi - jb_lo;
@@ -223,15 +226,15 @@ int gather_tiled_t(const void *e_prev, void *g, const int64_t *ent_ptr, const vo
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    // 2 CTAs fit per SM; aim for at least ~2 waves on 148 SMs before giving every CTA
-    // the full 1024-bin window
+    // 2 CTAs fit per SM (296 in flight); aim for at least ~8 waves before giving every
+    // CTA the full 1024-bin window, so that the tail of the grid stays short
     int warps_t = kWarpsT;
-    while (warps_t > 2 && n_cta * ceil_div(t_pad, (int64_t)warps_t * kSliceT) < 2 * 296)
+    while (warps_t > 2 && n_cta * ceil_div(t_pad, (int64_t)warps_t * kSliceT) < 8 * 296)
         warps_t /= 2;
     dim3 grid((unsigned)n_cta, (unsigned)ceil_div(t_pad, (int64_t)warps_t * kSliceT));
     k_gather_tma<T><<<grid, (kWarpsT + 1) * 32, smem, st>>>(
         (const T *)e_prev, (T *)g, ent_ptr, (const TileRecord<T> *)recs, n_patches, n_alloc,
-        n_blocks, n_dirs, b_lo, jb_lo, n_jb, n_classes, t_pad, ld, pad, warps_t);
+        n_blocks, n_dirs, b_lo, jb_lo, n_jb, n_classes, t_pad, ld, pad, warps_t, cta_order);
     return check_launch("k_gather_tma");
 }
 
@@ -251,7 +254,8 @@ int spb_tile_geometry(int dtype, int64_t *receivers_per_tile, int64_t *delay_buc
 }
 
 int spb_exchange_gather_tiled(const void *e_prev, void *g, const int64_t *ent_ptr,
-                              const void *recs, int64_t n_patches, int64_t n_alloc,
+                              const void *recs, const int32_t *cta_order,
+                              int64_t n_patches, int64_t n_alloc,
                               int64_t n_classes, int64_t n_dirs, int64_t n_bands,
                               int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi,
                               int64_t t_pad, int64_t ld, int64_t pad, int dtype,
@@ -266,10 +270,12 @@ int spb_exchange_gather_tiled(const void *e_prev, void *g, const int64_t *ent_pt
     SPB_REQUIRE(pad % kBucket == 0 && pad >= 2 * kBucket, "pad (use spb_exchange_layout)");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SPB_F64)
-        return gather_tiled_t<double>(e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_classes,
+        return gather_tiled_t<double>(e_prev, g, ent_ptr, recs, cta_order, n_patches, n_alloc,
+                                      n_classes,
                                       n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     if (dtype == SPB_F32)
-        return gather_tiled_t<float>(e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_classes,
+        return gather_tiled_t<float>(e_prev, g, ent_ptr, recs, cta_order, n_patches, n_alloc,
+                                     n_classes,
                                      n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     return fail(-1, "invalid argument", "dtype");
 }

@@ -121,13 +121,27 @@ class ShardedExchange:
         st = _lib.stream_ptr()
         if t.recs is not None and os.environ.get("SPB_GATHER", "tma") != "csr":
             _lib.call("spb_exchange_gather_tiled", prev, self.g, t.ent_ptr, t.recs,
-                      t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
+                      self.cta_order(), t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
                       b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad, code, st)
         else:
             _lib.call("spb_exchange_gather", prev, self.g, t.seg_ptr, t.src, t.wgt, t.dly,
                       t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
                       b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad, code, st)
         self._mix(cur, total, b_lo, b_hi)
+
+    def cta_order(self):
+        """Launch order of this rank's tiles: longest record lists first (LPT), so the
+        short tiles fill the tail of the grid."""
+        if getattr(self, "_cta_order", None) is None:
+            t = self.t
+            n_r = 8
+            n_blocks = -(-t.n_patches // n_r)
+            jb_lo, jb_hi = self.j_lo // n_r, -(-self.j_hi // n_r)
+            counts = (t.ent_ptr[1:] - t.ent_ptr[:-1]).view(t.n_classes, n_blocks)
+            local = counts[:, jb_lo:jb_hi].reshape(-1)
+            self._cta_order = torch.argsort(local, descending=True, stable=True).to(
+                torch.int32).contiguous()
+        return self._cta_order
 
     def _mix(self, cur, total, b_lo, b_hi):
         """Stage 2; with symmetric buffers it also delivers E_k to every rank."""

@@ -168,8 +168,16 @@ def test_tiled_and_csr_gather_agree_on_ragged_lists():
     st, code = _lib.stream_ptr(), _lib.I32(tables.dtype)
     _lib.call("spb_exchange_gather", prev, g1, tables.seg_ptr, tables.src, tables.wgt,
               tables.dly, n, n, c, d, b, 0, b, 0, n, t_pad, ld, pad, code, st)
-    _lib.call("spb_exchange_gather_tiled", prev, g2, tables.ent_ptr, tables.recs, n, n, c,
-              d, b, 0, b, 0, n, t_pad, ld, pad, code, st)
+    _lib.call("spb_exchange_gather_tiled", prev, g2, tables.ent_ptr, tables.recs, None, n, n,
+              c, d, b, 0, b, 0, n, t_pad, ld, pad, code, st)
+    # an explicit launch order (here: reversed) must not change anything
+    n_tiles = c * (-(-n // 8))
+    order = torch.arange(n_tiles - 1, -1, -1, dtype=torch.int32, device=dev)
+    g3 = torch.zeros_like(g1)
+    _lib.call("spb_exchange_gather_tiled", prev, g3, tables.ent_ptr, tables.recs, order, n, n,
+              c, d, b, 0, b, 0, n, t_pad, ld, pad, code, st)
+    torch.cuda.synchronize()
+    assert torch.equal(g2, g3)
     torch.cuda.synchronize()
     a, bb = g1[:, pad:pad + t_len], g2[:, pad:pad + t_len]
     assert torch.allclose(a, bb, rtol=1e-12, atol=1e-14)
@@ -216,7 +224,7 @@ def test_sharded_driver_matches_one_call_api(oracle):
     for _ in range(4):
         for lo, hi in ((lo0, hi0), (lo1, hi1)):
             for b in range(t.n_bands):           # one band at a time, like the pipeline
-                _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
+                _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs, None,
                           t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b, b + 1,
                           lo, hi, sx.t_pad, sx.ld, sx.pad, code, st)
                 _lib.call("spb_exchange_mix", sx.g, cur, sx.e_total, t.seg_ptr, t.coef,

@@ -1,0 +1,124 @@
+"""Host-side index bookkeeping of the exchange on CPU tensors: CSR segments and the
+tile records of the TMA gather are lossless re-encodings of the directed pair list;
+patch renumbering and source tiling keep it intact.  (No kernels run here; the
+library is only asked for its tile geometry.)"""
+import numpy as np
+import pytest
+import torch
+
+from sparrowpy_b200 import _lib, exchange, geometry, scenes
+
+
+def random_pairs(seed, n=61, d=3, c=4, m=2500, t_len=200):
+    gen = torch.Generator().manual_seed(seed)
+    sender = torch.randint(0, n, (m,), generator=gen)
+    receiver = torch.randint(0, n, (m,), generator=gen)
+    _, first = np.unique((sender * n + receiver).numpy(), return_index=True)
+    sel = torch.from_numpy(np.sort(first))
+    sender, receiver = sender[sel], receiver[sel]
+    m = sender.numel()
+    ff = torch.rand(m, generator=gen, dtype=torch.float64) + 0.01
+    delay = torch.randint(0, 260, (m,), generator=gen)      # some >= t_len: dropped
+    out_dir = torch.randint(0, d, (m,), generator=gen)
+    cls = torch.randint(0, c, (m,), generator=gen)
+    coef = torch.rand((c, d, 2), generator=gen, dtype=torch.float64)
+    return sender, receiver, ff, delay, out_dir, cls, coef, n, t_len
+
+
+def decode_records(t, dtype=np.float64):
+    """(class, receiver, src_row, delay, weight) tuples encoded in the tile records."""
+    n_r, bucket, rec_bytes = exchange.tile_geometry(t.dtype)
+    wsize = 8 if t.dtype == _lib.F64 else 4
+    recs = t.recs.numpy()
+    ent = t.ent_ptr.numpy()
+    n_blocks = -(-t.n_patches // n_r)
+    out = []
+    for tile in range(len(ent) - 1):
+        c, jb = divmod(tile, n_blocks)
+        for e in range(ent[tile], ent[tile + 1]):
+            raw = recs[e]
+            w = raw[:n_r * wsize].view(np.float64 if wsize == 8 else np.float32)
+            rel = raw[n_r * wsize:n_r * wsize + n_r]
+            src, packed = raw[n_r * wsize + n_r:].view(np.int32)
+            dmin, mask = int(packed) & 0xffffff, (int(packed) >> 24) & 0xff
+            assert dmin % bucket == 0
+            cur = None
+            for s in range(n_r):
+                if w[s] != 0:
+                    out.append((c, jb * n_r + s, int(src), dmin + int(rel[s]), float(w[s])))
+                    # the reload mask marks exactly the changes of shift among used slots
+                    assert bool(mask >> s & 1) == (cur != rel[s])
+                    cur = rel[s]
+                else:
+                    assert not (mask >> s & 1)
+                    assert cur is None or rel[s] == cur or True
+    return sorted(out)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_csr_and_tile_records_encode_the_same_pairs(dtype):
+    sender, receiver, ff, delay, out_dir, cls, coef, n, t_len = random_pairs(1)
+    t = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n, t_len,
+                                   dtype)
+    keep = delay < t_len
+    assert t.n_directed == sender.numel() and t.src.numel() == int(keep.sum())
+    assert t.max_delay == int(delay[keep].max())
+    cast = np.float64 if dtype == "f64" else np.float32
+    want = sorted((int(c), int(r), int(s) * t.n_dirs + int(o), int(dl), float(cast(w)))
+                  for c, r, s, o, dl, w in zip(cls[keep], receiver[keep], sender[keep],
+                                               out_dir[keep], delay[keep], ff[keep]))
+    # CSR
+    seg_ptr = t.seg_ptr.numpy()
+    got = []
+    for seg in range(len(seg_ptr) - 1):
+        c, j = divmod(seg, n)
+        for q in range(seg_ptr[seg], seg_ptr[seg + 1]):
+            got.append((c, j, int(t.src[q]), int(t.dly[q]), float(t.wgt[q])))
+    assert sorted(got) == want
+    # tile records
+    assert decode_records(t) == want
+
+
+def test_renumbering_and_source_tiling():
+    sender, receiver, ff, delay, out_dir, cls, coef, n, t_len = random_pairs(2)
+    gen = np.random.default_rng(0)
+    n_int = n + 11
+    rank = torch.from_numpy(gen.permutation(n_int)[:n].astype(np.int64))
+    t = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n, t_len,
+                                   "f64", rank=rank, n_internal=n_int)
+    assert (t.n_patches, t.n_user) == (n_int, n)
+    keep = delay < t_len
+    want = sorted((int(c), int(rank[r]), int(rank[s]) * t.n_dirs + int(o), int(dl), float(w))
+                  for c, r, s, o, dl, w in zip(cls[keep], receiver[keep], sender[keep],
+                                               out_dir[keep], delay[keep], ff[keep]))
+    assert decode_records(t) == want
+    x = torch.arange(n, dtype=torch.float64)
+    xi = t.to_internal(x)
+    assert xi.shape == (n_int,) and torch.equal(xi[rank], x) and float(xi.sum()) == float(x.sum())
+    t3 = t.tiled(3)
+    assert t3.n_bands == 3 * t.n_bands and t3.coef.shape == (t.n_classes, t.n_dirs, 6)
+    assert torch.equal(t3.coef[:, :, 2:4], t.coef) and t3.recs is t.recs
+
+
+def test_compact_order_is_a_balanced_numbering():
+    walls = scenes.street_canyon(0, 0.25)
+    pts, ids = geometry.process_patches(np.array([w[0] for w in walls]), 1.0)
+    for shards in (1, 2, 4, 8):
+        rank, n_int = geometry.compact_patch_order(pts, ids, n_shards=shards)
+        assert len(np.unique(rank)) == len(ids) and rank.max() < n_int
+        assert n_int % (8 * shards) == 0
+        size = n_int // shards
+        per_shard = np.bincount(rank // size, minlength=shards)
+        assert per_shard.max() - per_shard.min() <= max(16, 0.2 * per_shard.mean())
+    # tiles of 8 consecutive internal indices are spatially compact
+    rank, n_int = geometry.compact_patch_order(pts, ids)
+    cen = pts.mean(axis=1)
+    inv = -np.ones(n_int, int)
+    inv[rank] = np.arange(len(rank))
+    ext = []
+    for k in range(0, n_int, 8):
+        m = inv[k:k + 8]
+        m = m[m >= 0]
+        if len(m) > 1:
+            ext.append(np.ptp(cen[m], axis=0).max())
+    assert np.mean(ext) <= 3.0 + 1e-9        # 2 x 4 patches of 1 m: extent <= 3 m

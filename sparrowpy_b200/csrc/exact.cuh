@@ -6,35 +6,46 @@
 #pragma once
 #include "x87.cuh"
 
+// The predicates are plain C++: under nvcc they are device (and host) functions,
+// under g++ they compile for the host, where tests/native/exact_selftest.cpp checks
+// them against the CPU oracle on millions of cases.
+#if defined(__CUDACC__)
+#define SPB_FN __host__ SPB_FN
+#define SPB_FN_NOINLINE __host__ SPB_FN_NOINLINE
+#else
+#define SPB_FN inline
+#define SPB_FN_NOINLINE inline
+#endif
+
 namespace spb {
 namespace exact {
 
 constexpr double kEta = 1e-6;
 
-__device__ __forceinline__ double dot3(const double *a, const double *b) {
+SPB_FN double dot3(const double *a, const double *b) {
     double s = a[0] * b[0];
     s = fma(a[1], b[1], s);
     s = fma(a[2], b[2], s);
     return s;
 }
-__device__ __forceinline__ double dot2(const double *a, const double *b) {
+SPB_FN double dot2(const double *a, const double *b) {
     double s = a[0] * b[0];
     s = fma(a[1], b[1], s);
     return s;
 }
-__device__ __forceinline__ double nrm3(const double *v) { return x87::norm3(v[0], v[1], v[2]); }
-__device__ __forceinline__ double nrm2(const double *v) { return x87::norm2(v[0], v[1]); }
-__device__ __forceinline__ void sub3(const double *a, const double *b, double *o) {
+SPB_FN double nrm3(const double *v) { return x87::norm3(v[0], v[1], v[2]); }
+SPB_FN double nrm2(const double *v) { return x87::norm2(v[0], v[1]); }
+SPB_FN void sub3(const double *a, const double *b, double *o) {
     o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2];
 }
-__device__ __forceinline__ void cross3(const double *a, const double *b, double *o) {
+SPB_FN void cross3(const double *a, const double *b, double *o) {
     o[0] = a[1] * b[2] - a[2] * b[1];
     o[1] = a[2] * b[0] - a[0] * b[2];
     o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
 // reference geometry.py:498-559 with the default target (0,0,1)
-__device__ inline void rotation_matrix(const double *n, double R[9]) {
+SPB_FN void rotation_matrix(const double *n, double R[9]) {
     if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 1.0) {
         R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
         return;
@@ -80,7 +91,7 @@ struct Blocker {
 };
 constexpr int kBlockerDoubles = sizeof(Blocker) / sizeof(double);
 
-__device__ inline void make_blocker(const double *pts /*4x3*/, const double *n, Blocker &k) {
+SPB_FN void make_blocker(const double *pts /*4x3*/, const double *n, Blocker &k) {
     double R[9];
     rotation_matrix(n, R);
     for (int c = 0; c < 3; ++c) {
@@ -138,7 +149,7 @@ __device__ inline void make_blocker(const double *pts /*4x3*/, const double *n, 
 // geometry.py:658-686: winding count over the four sides for a query point that is
 // already rotated into the plane.  Out of line: it carries the x87 emulation and is
 // reached for a tiny fraction of the (pair, blocker) combinations only.
-__device__ __noinline__ bool point_in_polygon_sides(double ptx, double pty, const Blocker *kp) {
+SPB_FN_NOINLINE bool point_in_polygon_sides(double ptx, double pty, const Blocker *kp) {
     const Blocker &k = *kp;
     const double pt[2] = {ptx, pty};
     int count = 0;
@@ -181,7 +192,7 @@ __device__ __noinline__ bool point_in_polygon_sides(double ptx, double pty, cons
 //         hit); both vertical sides are hit in their interior, where
 //         |b-a0| + |b-a1| - |a1-a0| is pure rounding (~1e-15 << 1e-6), with
 //         d = (b_x - q_x) * nl_x of opposite signs (+1 and -1) -> count == 0.
-__device__ __forceinline__ double ray_clearance(double qx, double qy, const Blocker &k) {
+SPB_FN double ray_clearance(double qx, double qy, const Blocker &k) {
     const double c_ray = fmax(fmax(qy - k.ymax, k.ymin - qy), qx - k.xmax) - k.h;
     const double c_aa = fmin(fmin(qy - k.ymin, k.ymax - qy), k.xmin - qx) - 1e-7;
     return k.aa2d != 0.0 ? fmax(c_ray, c_aa) : c_ray;
@@ -189,14 +200,14 @@ __device__ __forceinline__ double ray_clearance(double qx, double qy, const Bloc
 constexpr double kClearGuard = 2e-9;   // absorbs the rounding of ray_clearance itself
 
 // geometry.py:645-686 for a point that passed the coplanarity test (:641)
-__device__ __forceinline__ bool point_in_polygon_2d(const double *p, const Blocker &k) {
+SPB_FN bool point_in_polygon_2d(const double *p, const Blocker &k) {
     const double ptx = dot3(k.r0, p), pty = dot3(k.r1, p);
     if (ray_clearance(ptx, pty, k) > kClearGuard) return false;
     return point_in_polygon_sides(ptx, pty, &k);
 }
 
 // geometry.py:614-686
-__device__ __forceinline__ bool point_in_polygon(const double *p, const Blocker &k) {
+SPB_FN bool point_in_polygon(const double *p, const Blocker &k) {
     double d0[3];
     sub3(p, k.s0, d0);
     if (fabs(dot3(d0, k.n)) > kEta) return false;
@@ -220,7 +231,7 @@ __device__ __forceinline__ bool point_in_polygon(const double *p, const Blocker 
 //        E -+ (dE/dp) v, at most eta*|v|/|dp| away from E.  If ray_clearance(E)
 //        exceeds that distance (+3e-9 for rounding), "hit in polygon" is False.
 //    v = B - A, vlen = |v| (any rounding), cull_ok = |v|^2 > 1e-6.
-__device__ __forceinline__ bool blocked(const double *A, const double *B, const double *v,
+SPB_FN bool blocked(const double *A, const double *B, const double *v,
                                         double vlen, bool cull_ok, const Blocker &k) {
     double wa[3], w[3];
     sub3(A, k.s0, wa);
@@ -272,7 +283,7 @@ __device__ __forceinline__ bool blocked(const double *A, const double *B, const 
 
 // numba `diff /= np.linalg.norm(diff)` followed by argmin of squared distances
 // (RadiosityFast.py:1304-1310, :1386-1389): first minimum wins.
-__device__ inline int nearest_direction(const double *to, const double *from,
+SPB_FN int nearest_direction(const double *to, const double *from,
                                         const double *dirs, int n_dirs) {
     double diff[3];
     sub3(to, from, diff);

@@ -220,12 +220,9 @@ int gather_tiled_t(const void *e_prev, void *g, const int64_t *ent_ptr, const vo
     if (n_cta == 0) return 0;
     SPB_REQUIRE(n_cta <= 2147483647LL, "too many tiles for one launch");
     const size_t smem = sizeof(Stage<T>) * kStages + 2 * kStages * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        SPB_CUDA(cudaFuncSetAttribute(k_gather_tma<T>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // per launch: the attribute is per device, and a process may drive several
+    SPB_CUDA(cudaFuncSetAttribute(k_gather_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
     // 2 CTAs fit per SM (296 in flight).  Fewer time slices per CTA leave consumer warps
     // idle (the ring is sized for the full window and registers cap residency at 2
     // CTAs), so the window is only narrowed when the grid would not even fill the

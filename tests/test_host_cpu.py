@@ -39,3 +39,20 @@ def test_scene_sizes():
     assert n_patches(scenes.ground_plane(-50, 50, -50, 50), 0.5) == 40000   # config 3
     for w in scenes.street_canyon() + scenes.city_block():
         geometry.Polygon(*w)                                         # planarity / normal asserts
+
+
+def test_visibility_predicate_shortcuts_match_oracle(tmp_path):
+    """exact.cuh (the device predicate with its result-preserving shortcuts) compiled for
+    the host and compared with the oracle's literal `_basic_visibility` on 800 k random,
+    coplanar and lattice-degenerate cases."""
+    obj = tmp_path / "sor.o"
+    exe = tmp_path / "exact_selftest"
+    flags = ["-O2", "-ffp-contract=off"]
+    subprocess.check_call(["gcc", *flags, "-std=gnu11", "-c",
+                           os.path.join(REPO, "oracle", "sparrow_oracle.c"), "-o", str(obj)])
+    subprocess.check_call(["g++", *flags, "-o", str(exe),
+                           os.path.join(REPO, "tests", "native", "exact_selftest.cpp"),
+                           str(obj), "-lm"])
+    out = subprocess.run([str(exe), "200000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert " 0 mismatches" in out.stdout

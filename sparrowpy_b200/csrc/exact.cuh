@@ -10,8 +10,8 @@
 // under g++ they compile for the host, where tests/native/exact_selftest.cpp checks
 // them against the CPU oracle on millions of cases.
 #if defined(__CUDACC__)
-#define SPB_FN __host__ SPB_FN
-#define SPB_FN_NOINLINE __host__ SPB_FN_NOINLINE
+#define SPB_FN __host__ __device__ __forceinline__
+#define SPB_FN_NOINLINE __host__ __device__ __noinline__
 #else
 #define SPB_FN inline
 #define SPB_FN_NOINLINE inline

@@ -208,12 +208,26 @@ def time_bake(rad, n_pairs):
     from sparrowpy_b200 import _lib
     vis_ms = timed(lambda: _lib.call("spb_visibility_p2p", g["center"], n, blockers, n, vis,
                                      _lib.stream_ptr()), reps=1)
+    # hierarchical variant (the one bake_geometry uses): tables built once, kernel timed
+    import numpy as _np
+    groups, members, bin_ptr, bin_items = bake.build_groups(
+        blockers.cpu().numpy().reshape(n, -1), rad._patch_to_wall_ids)
+    dev = g["center"].device
+    gt, mt, bp, bi = (torch.from_numpy(_np.ascontiguousarray(a)).to(dev)
+                      for a in (groups, members, bin_ptr, bin_items))
+    vis_g = torch.empty_like(vis)
+    vis_grouped_ms = timed(lambda: _lib.call(
+        "spb_visibility_p2p_grouped", g["center"], n, blockers, gt, len(groups), mt, bp, bi,
+        vis_g, _lib.stream_ptr()), reps=1)
+    same = bool(torch.equal(vis, vis_g))
     pairs = rad._baked["pairs"]
     ff_ms = timed(lambda: bake.form_factors(g["points"], g["normal"], g["area"], pairs))
     pair_blocker = 0.5 * n * (n - 1) * n
     fp64_peak = 37e12
     return {
-        "visibility_ms": vis_ms, "pair_blocker_tests_per_s": pair_blocker / (vis_ms * 1e-3),
+        "visibility_ms": vis_grouped_ms, "visibility_groups": int(len(groups)),
+        "visibility_bruteforce_ms": vis_ms, "visibility_grouped_equals_bruteforce": same,
+        "pair_blocker_tests_per_s": pair_blocker / (vis_ms * 1e-3),
         "visibility_fp64_frac_nominal": 25.0 * pair_blocker / (vis_ms * 1e-3) / fp64_peak,
         "form_factor_ms": ff_ms, "form_factor_pairs_per_s": n_pairs / (ff_ms * 1e-3),
         "form_factor_fp64_frac_nominal": 3300.0 * n_pairs / (ff_ms * 1e-3) / fp64_peak,

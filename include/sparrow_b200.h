@@ -201,6 +201,27 @@ int spb_make_blockers(const double *surf_points, const double *surf_normals, int
 int spb_visibility_p2p(const double *centers, int64_t n, const void *blockers, int64_t m,
                        uint8_t *vis, void *stream);
 
+/* Same result as spb_visibility_p2p, evaluated hierarchically: the blockers are
+ * grouped by plane (the patches of one wall), a group is decided with one evaluation
+ * of the plane quantities, and only the members whose polygon the plane hit can touch
+ * (found through bins along the in-plane y axis) are evaluated individually.
+ * O(N^2 * walls) instead of O(N^3).  Tables from sparrowpy_b200.bake.build_groups:
+ * groups: n_groups records of spb_group_bytes() bytes; members: blocker indices;
+ * bin_ptr / bin_items: CSR of the bins of all groups. */
+size_t spb_group_bytes(void);
+int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blockers,
+                               const void *groups, int64_t n_groups, const int32_t *members,
+                               const int32_t *bin_ptr, const int32_t *bin_items, uint8_t *vis,
+                               void *stream);
+/* host twins of spb_make_blockers / spb_visibility_p2p_grouped (HOST pointers): the
+ * same predicates compiled for the CPU; used by the CPU tests only */
+int spb_make_blockers_host(const double *surf_points_h, const double *surf_normals_h,
+                           int64_t m, void *blockers_h);
+int spb_visibility_p2p_grouped_host(const double *centers_h, int64_t n, const void *blockers_h,
+                                    const void *groups_h, int64_t n_groups,
+                                    const int32_t *members_h, const int32_t *bin_ptr_h,
+                                    const int32_t *bin_items_h, uint8_t *vis_h);
+
 /* `_check_point2patch_visibility` (geometry.py:799-839) for a batch of points:
  * vis[r,j] ([R,N] uint8). */
 int spb_visibility_pt2p(const double *points, int64_t n_points, const double *centers,

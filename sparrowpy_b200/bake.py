@@ -168,3 +168,122 @@ def probe_basic_visibility(a, b, surf_points, surf_normals):
     _lib.call("spb_probe_basic_visibility", a, b, blockers, n, outs[0], outs[1], outs[2],
               _lib.stream_ptr())
     return [o.bool() for o in outs]
+
+
+# ---------------------------------------------------------------------------
+# hierarchical visibility (csrc/vis_group.cuh)
+# ---------------------------------------------------------------------------
+_BLK = dict(n=slice(0, 3), s0=slice(3, 6), r0=slice(6, 9), r1=slice(9, 12), xmin=32, xmax=33,
+            ymin=34, ymax=35, h=36, aa2d=37)
+_BIN_MARGIN = 2e-3          # members are binned with this margin around their ray band
+
+
+def build_groups(blockers_np, group_ids):
+    """Group table for ``spb_visibility_p2p_grouped`` (host-side index bookkeeping).
+
+    blockers_np: (M, 38) float64 view of the Blocker records; group_ids: (M,) the wall
+    each blocker belongs to.  A wall becomes one group when all its blockers share the
+    bitwise-same normal (hence rotation) and their first vertices lie in one plane to
+    within 1e-12; otherwise its blockers become singleton groups (always correct, just
+    not accelerated).  Returns numpy arrays (groups uint8 (G, group_bytes), members
+    int32, bin_ptr int32, bin_items int32).
+    """
+    import numpy as np
+    lib = _lib.load()
+    lib.spb_group_bytes.restype = ctypes.c_size_t
+    gbytes = int(lib.spb_group_bytes())
+    assert gbytes == 144, gbytes
+    blk = np.ascontiguousarray(blockers_np, dtype=np.float64)
+    ids = np.asarray(group_ids)
+    member_lists = []
+    for w in np.unique(ids):
+        idx = np.nonzero(ids == w)[0]
+        key = blk[idx][:, :12].copy()
+        key[:, 3:6] = 0.0                                 # n, r0, r1 must be bitwise equal
+        same = (key.view(np.uint64) == key[:1].view(np.uint64)).all()
+        n0, s00 = blk[idx[0], _BLK["n"]], blk[idx[0], _BLK["s0"]]
+        dev = np.abs((blk[idx][:, _BLK["s0"]] - s00) @ n0).max()
+        if same and dev <= 1e-12:
+            member_lists.append((idx, float(dev) + 1e-13))
+        else:
+            member_lists.extend((idx[k:k + 1], 0.0) for k in range(len(idx)))
+    groups = np.zeros((len(member_lists), gbytes), dtype=np.uint8)
+    gd = groups.view(np.float64).reshape(len(member_lists), gbytes // 8)
+    gi = groups.view(np.int32).reshape(len(member_lists), gbytes // 4)
+    members, bin_ptr, bin_items = [], [0], []
+    for g, (idx, dev) in enumerate(member_lists):
+        b = blk[idx]
+        lo = b[:, _BLK["ymin"]] - b[:, _BLK["h"]] - _BIN_MARGIN
+        hi = b[:, _BLK["ymax"]] + b[:, _BLK["h"]] + _BIN_MARGIN
+        bin_h = float((hi - lo).max())
+        y0 = float(lo.min())
+        n_bins = int(np.floor((hi.max() - y0) / bin_h)) + 1
+        first = np.floor((lo - y0) / bin_h).astype(np.int64)
+        last = np.minimum(np.floor((hi - y0) / bin_h).astype(np.int64), n_bins - 1)
+        per_bin = [[] for _ in range(n_bins)]
+        for k in range(len(idx)):
+            # one extra bin on each side guards the rounding of the kernel's bin index
+            for bb in range(max(int(first[k]) - 1, 0), min(int(last[k]) + 1, n_bins - 1) + 1):
+                per_bin[bb].append(int(idx[k]))
+        gd[g, 0:3], gd[g, 3:6] = b[0, _BLK["n"]], b[0, _BLK["s0"]]
+        gd[g, 6:9], gd[g, 9:12] = b[0, _BLK["r0"]], b[0, _BLK["r1"]]
+        gd[g, 12], gd[g, 13], gd[g, 14] = dev, y0, 1.0 / bin_h
+        gi[g, 32], gi[g, 33] = n_bins, len(bin_ptr) - 1
+        gi[g, 34], gi[g, 35] = len(members), len(members) + len(idx)
+        members.extend(int(k) for k in idx)
+        for items in per_bin:
+            bin_items.extend(items)
+            bin_ptr.append(len(bin_items))
+    return (groups, np.asarray(members, np.int32), np.asarray(bin_ptr, np.int32),
+            np.asarray(bin_items if bin_items else [0], np.int32))
+
+
+def make_blockers_host(surf_points, surf_normals):
+    """CPU twin of make_blockers (numpy in, (M, 38) float64 out) -- tests only."""
+    import numpy as np
+    lib = _lib.load()
+    pts = np.ascontiguousarray(surf_points, dtype=np.float64)
+    nrm = np.ascontiguousarray(surf_normals, dtype=np.float64)
+    lib.spb_blocker_bytes.restype = ctypes.c_size_t
+    m = pts.shape[0]
+    out = np.zeros((m, lib.spb_blocker_bytes(ctypes.c_int64(m)) // 8 // max(m, 1)))
+    rc = lib.spb_make_blockers_host(pts.ctypes.data_as(ctypes.c_void_p),
+                                    nrm.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(m),
+                                    out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return out
+
+
+def visibility_p2p_grouped_host(centers, surf_normals, surf_points, group_ids):
+    """CPU twin of the grouped visibility kernel (numpy) -- tests only."""
+    import numpy as np
+    lib = _lib.load()
+    cen = np.ascontiguousarray(centers, dtype=np.float64)
+    blk = make_blockers_host(surf_points, surf_normals)
+    groups, members, bin_ptr, bin_items = build_groups(blk, group_ids)
+    n = cen.shape[0]
+    vis = np.zeros((n, n), np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    rc = lib.spb_visibility_p2p_grouped_host(p(cen), ctypes.c_int64(n), p(blk), p(groups),
+                                             ctypes.c_int64(len(groups)), p(members),
+                                             p(bin_ptr), p(bin_items), p(vis))
+    assert rc == 0
+    return vis.astype(bool)
+
+
+def visibility_p2p_grouped(centers, surf_normals, surf_points, group_ids):
+    """``geometry._check_patch2patch_visibility`` (geometry.py:750-797), hierarchical:
+    same (N, N) bool matrix as :func:`visibility_p2p` in O(N^2 * walls)."""
+    centers = _dev(centers, torch.float64)
+    n = centers.shape[0]
+    blockers = make_blockers(surf_points, surf_normals)
+    m = surf_points.shape[0]
+    blk_np = blockers.cpu().numpy().reshape(m, -1)
+    groups, members, bin_ptr, bin_items = build_groups(
+        blk_np, group_ids.cpu().numpy() if isinstance(group_ids, torch.Tensor) else group_ids)
+    dev = centers.device
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    vis = torch.empty((n, n), dtype=torch.uint8, device=dev)
+    _lib.call("spb_visibility_p2p_grouped", centers, n, blockers, t(groups), len(groups),
+              t(members), t(bin_ptr), t(bin_items), vis, _lib.stream_ptr())
+    return vis.bool()

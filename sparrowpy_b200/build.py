@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libsparrow_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-          "-Xcompiler", "-fno-fast-math"]
+          "-Xcompiler", "-fno-fast-math", "-Xcompiler", "-ffp-contract=off"]
 
 # (source, extra flags).  The bake kernels must reproduce the reference's
 # rounding model bit for bit: no FMA contraction there (explicit fma() only).

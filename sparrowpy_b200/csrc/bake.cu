@@ -11,6 +11,7 @@
 // direction indices, directional source energy).
 #include "common.cuh"
 #include "exact.cuh"
+#include "vis_group.cuh"
 
 namespace spb {
 
@@ -193,6 +194,45 @@ k_vis_pt2p(const double *__restrict__ points, const double *__restrict__ centers
     }
     const bool v = visible_against_all(A, B, active, blockers, m, -1, -1, sm);
     if (active) vis[r * n + j] = v ? 1 : 0;
+}
+
+// hierarchical variant: one CTA per (row i, chunk of j), loop over blocker groups
+// (vis_group.cuh); the group headers are staged in shared memory when they fit
+constexpr int kMaxGroupsSmem = 256;
+
+__global__ void __launch_bounds__(kVisThreads)
+k_vis_p2p_grouped(const double *__restrict__ centers, int64_t n,
+                  const Blocker *__restrict__ blockers, const exact::Group *__restrict__ groups,
+                  int32_t n_groups, const int32_t *__restrict__ members,
+                  const int32_t *__restrict__ bin_ptr, const int32_t *__restrict__ bin_items,
+                  int64_t chunks_per_row, uint8_t *__restrict__ vis) {
+    __shared__ exact::Group sg[kMaxGroupsSmem];
+    const int64_t i = blockIdx.x / chunks_per_row;
+    const int64_t j0 = (blockIdx.x % chunks_per_row) * kVisThreads;
+    if (j0 + kVisThreads - 1 <= i) return;
+    const bool staged = n_groups <= kMaxGroupsSmem;
+    if (staged) {
+        const double *src = reinterpret_cast<const double *>(groups);
+        double *dst = reinterpret_cast<double *>(sg);
+        const int words = n_groups * (int)(sizeof(exact::Group) / sizeof(double));
+        for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int64_t j = j0 + threadIdx.x;
+    if (!(j > i && j < n)) return;
+    double A[3], B[3], v[3];
+    for (int k = 0; k < 3; ++k) { A[k] = centers[3 * i + k]; B[k] = centers[3 * j + k]; }
+    exact::sub3(B, A, v);
+    const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double vlen = sqrt(vv);
+    const bool cull_ok = vv > 1e-6;
+    bool visible = true;
+    for (int32_t g = 0; g < n_groups && visible; ++g) {
+        const exact::Group &grp = staged ? sg[g] : groups[g];
+        visible = !exact::group_blocked(A, B, v, vlen, cull_ok, grp, blockers, members, bin_ptr,
+                                        bin_items);
+    }
+    vis[i * n + j] = visible ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -628,6 +668,64 @@ int spb_visibility_p2p(const double *centers, int64_t n, const void *blockers, i
     k_vis_p2p<<<(unsigned)(n * chunks), kVisThreads, 0, st>>>(
         centers, n, (const Blocker *)blockers, m, chunks, vis);
     return check_launch("k_vis_p2p");
+}
+
+int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blockers,
+                               const void *groups, int64_t n_groups, const int32_t *members,
+                               const int32_t *bin_ptr, const int32_t *bin_items, uint8_t *vis,
+                               void *stream) {
+    SPB_REQUIRE(centers && vis && blockers && groups && members && bin_ptr && bin_items,
+                "null pointer");
+    SPB_REQUIRE(n_groups >= 0 && n_groups <= 2147483647LL, "n_groups");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPB_CUDA(cudaMemsetAsync(vis, 0, (size_t)n * n, st));
+    if (n < 2) return 0;
+    const int64_t chunks = ceil_div(n, kVisThreads);
+    SPB_REQUIRE(n * chunks <= 2147483647LL, "too many patches for one launch");
+    k_vis_p2p_grouped<<<(unsigned)(n * chunks), kVisThreads, 0, st>>>(
+        centers, n, (const Blocker *)blockers, (const exact::Group *)groups, (int32_t)n_groups,
+        members, bin_ptr, bin_items, chunks, vis);
+    return check_launch("k_vis_p2p_grouped");
+}
+
+size_t spb_group_bytes(void) { return sizeof(exact::Group); }
+
+/* Host twins (HOST pointers) of make_blockers and the grouped visibility: the same
+ * predicates compiled for the CPU, used by the CPU test-suite to check the grouping
+ * logic and its Python table builder against the oracle without a GPU. */
+int spb_make_blockers_host(const double *surf_points_h, const double *surf_normals_h,
+                           int64_t m, void *blockers_h) {
+    SPB_REQUIRE(surf_points_h && surf_normals_h && blockers_h, "null pointer");
+    Blocker *out = (Blocker *)blockers_h;
+    for (int64_t s = 0; s < m; ++s)
+        exact::make_blocker(surf_points_h + 12 * s, surf_normals_h + 3 * s, out[s]);
+    return 0;
+}
+
+int spb_visibility_p2p_grouped_host(const double *centers_h, int64_t n, const void *blockers_h,
+                                    const void *groups_h, int64_t n_groups,
+                                    const int32_t *members_h, const int32_t *bin_ptr_h,
+                                    const int32_t *bin_items_h, uint8_t *vis_h) {
+    SPB_REQUIRE(centers_h && vis_h && blockers_h && groups_h, "null pointer");
+    const Blocker *blockers = (const Blocker *)blockers_h;
+    const exact::Group *groups = (const exact::Group *)groups_h;
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = 0; j < n; ++j) {
+            uint8_t out = 0;
+            if (j > i) {
+                const double *A = centers_h + 3 * i, *B = centers_h + 3 * j;
+                double v[3];
+                exact::sub3(B, A, v);
+                const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+                bool visible = true;
+                for (int64_t g = 0; g < n_groups && visible; ++g)
+                    visible = !exact::group_blocked(A, B, v, sqrt(vv), vv > 1e-6, groups[g],
+                                                    blockers, members_h, bin_ptr_h, bin_items_h);
+                out = visible ? 1 : 0;
+            }
+            vis_h[i * n + j] = out;
+        }
+    return 0;
 }
 
 int spb_visibility_pt2p(const double *points, int64_t n_points, const double *centers,

@@ -1,0 +1,135 @@
+// Hierarchical (per-wall) visibility: the conjunction over all blocking patches
+//     vis(A, B) = AND_k  not blocked(A, B, patch_k)           (geometry.py:786-795)
+// evaluated group by group, where a group is a set of coplanar blockers with the
+// bitwise-same normal (the patches of one wall).  For a group the plane quantities
+// of `_basic_visibility` are (up to the tiny, measured deviation `plane_dev` of the
+// members' first vertices from the common plane) the same for every member, so one
+// evaluation decides the whole group in the common cases:
+//
+//   * both end points clearly off the plane: no plane hit, or a hit clearly outside
+//     the open segment -> no member blocks (rule (a) of exact::blocked);
+//   * otherwise the only members that can block are those whose polygon the plane hit
+//     (or the in-plane end point) can be "in": every other member has
+//     exact::ray_clearance > the distance the member's own hit can differ from the
+//     group's.  The members are binned along the in-plane y axis, so those candidates
+//     are found by scanning one bin; each candidate is then evaluated with the exact
+//     per-blocker predicate exact::blocked.
+//
+// Whenever a bound needed for these arguments does not hold (end point within the
+// deviation of the eta threshold, grazing segment, huge segment) the group is simply
+// evaluated member by member.  The result is therefore identical to the brute-force
+// conjunction; tests/native/exact_selftest.cpp and tests/test_visgroup_cpu.py check
+// that on the host, the GPU tests on the device.
+#pragma once
+#include "exact.cuh"
+
+namespace spb {
+namespace exact {
+
+struct Group {
+    double n[3];         // common plane normal (bitwise equal for all members)
+    double s0[3];        // first vertex of the first member
+    double r0[3];        // rotation rows (functions of n only)
+    double r1[3];
+    double plane_dev;    // max_k |DOT(S0_k - s0, n)| over the members (0 for lattices)
+    double y0;           // lower edge of bin 0 (in-plane y)
+    double inv_bin_h;    // 1 / bin height
+    double pad_;
+    int32_t n_bins;
+    int32_t bin_ptr0;    // this group's bins are bin_ptr[bin_ptr0 .. bin_ptr0 + n_bins]
+    int32_t m0, m1;      // members[m0 .. m1) = blocker indices of the group
+};
+
+constexpr double kGroupMargin = 1e-3;    // how far a member's hit may differ from the group's
+
+// every member of the group, one by one (always correct)
+SPB_FN bool group_blocked_bruteforce(const double *A, const double *B, const double *v,
+                                     double vlen, bool cull_ok, const Group &g,
+                                     const Blocker *blockers, const int32_t *members) {
+    for (int32_t q = g.m0; q < g.m1; ++q)
+        if (blocked(A, B, v, vlen, cull_ok, blockers[members[q]])) return true;
+    return false;
+}
+
+// members whose polygon a point within kGroupMargin of (qx, qy) could be "in"
+SPB_FN bool group_blocked_near(const double *A, const double *B, const double *v, double vlen,
+                               bool cull_ok, const Group &g, double qx, double qy,
+                               const Blocker *blockers, const int32_t *bin_ptr,
+                               const int32_t *bin_items) {
+    const double fb = (qy - g.y0) * g.inv_bin_h;
+    if (!(fb > -1.0) || !(fb < (double)g.n_bins + 1.0)) return false;   // outside every band
+    int32_t bin = (int32_t)floor(fb);
+    bin = bin < 0 ? 0 : (bin >= g.n_bins ? g.n_bins - 1 : bin);
+    const int32_t p0 = bin_ptr[g.bin_ptr0 + bin], p1 = bin_ptr[g.bin_ptr0 + bin + 1];
+    for (int32_t p = p0; p < p1; ++p) {
+        const Blocker &k = blockers[bin_items[p]];
+        if (ray_clearance(qx, qy, k) > kGroupMargin + kClearGuard) continue;
+        if (blocked(A, B, v, vlen, cull_ok, k)) return true;
+    }
+    return false;
+}
+
+// does any member of the group block the segment A-B?   v = B - A, vlen = |v|
+SPB_FN bool group_blocked(const double *A, const double *B, const double *v, double vlen,
+                          bool cull_ok, const Group &g, const Blocker *blockers,
+                          const int32_t *members, const int32_t *bin_ptr,
+                          const int32_t *bin_items) {
+    double wa[3], w[3];
+    sub3(A, g.s0, wa);
+    sub3(B, g.s0, w);
+    const double dA = dot3(wa, g.n);
+    const double dB = dot3(w, g.n);
+    const double dp = dot3(v, g.n);            // identical for every member
+    const double dev = g.plane_dev + 1e-11;    // |dE_k - dE_group| <= dev for E in {A, B}
+    const bool offA = fabs(dA) > kEta + dev, offB = fabs(dB) > kEta + dev;
+    const bool inplA = fabs(dA) < kEta - dev, inplB = fabs(dB) < kEta - dev;
+    if (!(offA || inplA) || !(offB || inplB) || !cull_ok || !(vlen < 1e4))
+        return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
+
+    if (offA && offB) {
+        // neither end point lies in any member's plane
+        if (!(fabs(dp) > 1e-6)) return false;                       // no plane hit at all
+        const double u = -dB;
+        const bool outside = dp > 0 ? (u > 3e-3 * dp || u < -1.003 * dp)
+                                    : (u < 3e-3 * dp || u > -1.003 * dp);
+        // member hit parameters differ from the group's by <= dev/|dp| <= ~1e-6
+        if (outside) return false;
+        const double shift = dev * vlen / fabs(dp) + 1e-9;          // |hit_k - hit_group|
+        if (!(shift < kGroupMargin))
+            return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
+        const double fac = -(dB / dp);
+        const double pt[3] = {(w[0] + g.s0[0]) + fac * v[0], (w[1] + g.s0[1]) + fac * v[1],
+                              (w[2] + g.s0[2]) + fac * v[2]};
+        return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, pt), dot3(g.r1, pt),
+                                  blockers, bin_ptr, bin_items);
+    }
+    if (inplA && inplB) {
+        // both end points in the plane: a member blocks only if an end point is in its
+        // polygon -- unless there is a "plane hit" with |dp| > 1e-6 (dp ~ dB - dA <= 2e-6)
+        if (fabs(dp) > 1e-6)
+            return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
+        if (group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, A), dot3(g.r1, A), blockers,
+                               bin_ptr, bin_items))
+            return true;
+        return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, B), dot3(g.r1, B),
+                                  blockers, bin_ptr, bin_items);
+    }
+    // exactly one end point E in the plane, the other clearly off it: a member blocks
+    // only if E is in its polygon, or the plane hit -- within eta*|v|/|dp| of E -- is
+    // (rule (b) of exact::blocked)
+    if (!(fabs(dp) > 1e-6)) {
+        // no plane hit: only "E in the polygon" can block
+        const double *E = inplA ? A : B;
+        return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, E), dot3(g.r1, E),
+                                  blockers, bin_ptr, bin_items);
+    }
+    const double slack = (kEta + dev) * vlen / fabs(dp) + 3e-9;
+    if (!(slack < kGroupMargin))
+        return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
+    const double *E = inplA ? A : B;
+    return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, E), dot3(g.r1, E), blockers,
+                              bin_ptr, bin_items);
+}
+
+}  // namespace exact
+}  // namespace spb

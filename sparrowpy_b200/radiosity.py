@@ -13,6 +13,8 @@ built when the attribute is read.
 There is no CPU fallback: without the CUDA library and a CUDA device every compute
 method raises ``SparrowB200Error``.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -219,7 +221,13 @@ class DirectionalRadiosityFast:
         """Bake the geometry: visibility, form factors, BRDF direction tables."""
         g = self._geom()
         dev = self._device
-        vis = bake.visibility_p2p(g["center"], g["normal"], g["points"])
+        # blockers = the patches themselves (RadiosityFast.py:374-375); grouped by wall
+        # the conjunction over blockers is evaluated hierarchically (same result)
+        if os.environ.get("SPB_VISIBILITY", "grouped") == "brute":
+            vis = bake.visibility_p2p(g["center"], g["normal"], g["points"])
+        else:
+            vis = bake.visibility_p2p_grouped(g["center"], g["normal"], g["points"],
+                                              self._patch_to_wall_ids)
         pairs = bake.visible_pairs(vis)
         ff, _ = bake.form_factors(g["points"], g["normal"], g["area"], pairs)
         with_brdf = self._brdf_incoming_directions is not None

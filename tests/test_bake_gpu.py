@@ -133,3 +133,33 @@ def test_scene_bake_matches_reference(oracle, name):
     assert np.array_equal(rf["rdir"].cpu().numpy(), g["receiver_dir_index"])
     assert np.array_equal(rf["delay"].cpu().numpy(), g["receiver_delays"])
     assert rel_err(rf["factor"].cpu().numpy(), g["receiver_factor"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_grouped_visibility_equals_bruteforce_and_reference(name):
+    """Hierarchical (per-wall) visibility kernel: same matrix as the brute-force kernel
+    and as the reference."""
+    from sparrowpy_b200 import bake
+    g = load_golden(name)
+    n = len(g["patches_center"])
+    cen, nrm, pts = T(g["patches_center"]), T(g["patches_normal"]), T(g["patches_points"])
+    brute = bake.visibility_p2p(cen, nrm, pts)
+    grouped = bake.visibility_p2p_grouped(cen, nrm, pts, g["patch_to_wall_ids"])
+    gold = np.unpackbits(g["visibility"])[:n * n].reshape(n, n).astype(bool)
+    assert torch.equal(brute, grouped)
+    assert np.array_equal(grouped.cpu().numpy(), gold)
+
+
+def test_grouped_visibility_full_size_c2():
+    """N = 3700: grouped == brute force on the whole matrix."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import bake, geometry, scenes
+    walls = scenes.shoebox(5, 6, 4)
+    wp = np.array([w[0] for w in walls])
+    wn = np.array([w[2] for w in walls])
+    pts, ids = geometry.process_patches(wp, 0.2)
+    cen = geometry.calculate_center(pts)
+    brute = bake.visibility_p2p(T(cen), T(wn[ids]), T(pts))
+    grouped = bake.visibility_p2p_grouped(T(cen), T(wn[ids]), T(pts), ids)
+    assert torch.equal(brute, grouped)
+    assert int(grouped.sum()) == 5672500

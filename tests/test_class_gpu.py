@@ -225,3 +225,33 @@ def test_multi_source_batch_equals_single_sources():
     rad.init_source_energy(pf.Coordinates(*srcs[1]))
     rad.calculate_energy_exchange(c, dt, dur, max_reflection_order=0, recalculate=True)
     assert rel_err(batch._energy_exchange_etc[1], rad._energy_exchange_etc) < 1e-13
+
+
+def test_ground_plane_multi_source_multi_receiver(oracle):
+    """Config-3 analogue at test size (BASELINE.json: one ground plane, order 0,
+    several sources and receivers; reference tests/
+    test_DRadiosityFast_infinite_diffuse_plane.py:59-90): coplanar patches never see
+    each other (P = 0), so the ETC is initial energy + receiver collection only."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf, scenes
+    walls = scenes.ground_plane(-5, 5, -5, 5)
+    rad = sp.DirectionalRadiosityFast.from_polygon([sp.Polygon(*w) for w in walls], 0.5)
+    assert rad.n_patches == 400
+    rad.bake_geometry()
+    assert rad._visible_patches.shape == (0, 2) and not rad.visibility_matrix.any()
+    rng = np.random.default_rng(0)
+    srcs = np.column_stack([rng.uniform(-4, 4, 3), rng.uniform(-4, 4, 3), rng.uniform(1, 5, 3)])
+    rcvs = np.column_stack([rng.uniform(-4, 4, 4), rng.uniform(-4, 4, 4), rng.uniform(1, 5, 4)])
+    c, dt, dur = 343.2, 1e-3, 0.08
+    rad.init_source_energy_batch(pf.Coordinates.from_cartesian(srcs))
+    rad.calculate_energy_exchange(c, dt, dur, max_reflection_order=0)
+    mono = rad.collect_energy_receiver_mono(pf.Coordinates.from_cartesian(rcvs)).time
+    assert mono.shape == (3, 4, 1, 80)
+    wp = np.array([w[0] for w in walls])
+    wn = np.array([w[2] for w in walls])
+    one = np.array([[[0.0, 0.0, 1.0]]])
+    for s in range(3):
+        ref = oracle.pipeline(wp, wn, 0.5, srcs[s], rcvs, c, dt, dur, 0, np.zeros(1), one, one,
+                              np.full((1, 1, 1, 1), np.pi), np.zeros(1, np.int64))
+        assert rel_err(mono[s], ref["etc_receiver_mono"]) < 1e-6
+        assert rel_err(rad._energy_exchange_etc[s], ref["etc"]) < 1e-6

@@ -69,11 +69,14 @@ def form_factors(points, normals, areas, pairs):
     p = pairs.shape[0]
     ff = torch.zeros(p, dtype=torch.float64, device=points.device)
     flag = torch.zeros(p, dtype=torch.uint8, device=points.device)
+    if p == 0:                       # e.g. a single plane: coplanar patches never see each other
+        return ff, flag.bool()
     _lib.call("spb_form_factors_stokes", points, areas, pairs, p, ff, flag,
               _lib.stream_ptr())
     todo = torch.nonzero(flag).reshape(-1).contiguous()
-    _lib.call("spb_form_factors_nusselt", points, normals, pairs, todo, todo.numel(), ff,
-              _lib.stream_ptr())
+    if todo.numel():
+        _lib.call("spb_form_factors_nusselt", points, normals, pairs, todo, todo.numel(), ff,
+                  _lib.stream_ptr())
     return ff, flag.bool()
 
 
@@ -92,6 +95,8 @@ def pair_geometry(centers, patch_to_wall, pairs, vi, vo):
     in_dir = torch.empty(2 * p, dtype=torch.int32, device=dev)
     n_in = 1 if vi is None else vi.shape[1]
     n_out = 1 if vo is None else vo.shape[1]
+    if p == 0:
+        return dist, out_dir, in_dir
     _lib.call("spb_pair_geometry", centers, _dev(patch_to_wall, torch.int64), pairs, p,
               None if vi is None else _dev(vi, torch.float64), n_in,
               None if vo is None else _dev(vo, torch.float64), n_out, dist, out_dir,
@@ -103,6 +108,8 @@ def delay_bins(dist, speed_of_sound, dt):
     """``int(d / c / dt)`` (RadiosityFast.py:1067-1068, :1135-1136): int32."""
     dist = _dev(dist, torch.float64)
     out = torch.empty(dist.shape, dtype=torch.int32, device=dist.device)
+    if dist.numel() == 0:
+        return out
     _lib.call("spb_delay_bins", dist, dist.numel(), float(speed_of_sound), float(dt), out,
               _lib.stream_ptr())
     return out

@@ -248,7 +248,8 @@ def main():
                     choices=sorted(CONFIGS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--gather", default=os.environ.get("SPB_GATHER", "tma"),
-                    choices=["tma", "csr"], help="stage-1 kernel: TMA-staged tiles or CSR")
+                    choices=["tma", "win", "csr"],
+                    help="stage-1 kernel: TMA-staged tiles, register windows (f64) or CSR")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
@@ -307,7 +308,11 @@ def main():
         cst = torch.cuda.current_stream()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(cst)
-        if args.gather == "tma":
+        if t.win_recs is not None and args.gather == "win":
+            _lib.call("spb_exchange_gather_window", prev, sx.g, t.win_ptr, t.win_recs,
+                      sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands,
+                      b_lo, b_hi, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, t.win_w, c32, sp)
+        elif args.gather != "csr":
             _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
                       sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
                       sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32, sp)
@@ -385,7 +390,9 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic,
-                "kernel": "k_gather_tma" if args.gather == "tma" else "k_gather",
+                "kernel": ("k_gather_win" if tables.win_recs is not None and
+                           args.gather == "win" else
+                           "k_gather" if args.gather == "csr" else "k_gather_tma"),
                 "peak_source": peak_src, "avg_launch_ms": gather_avg_ms,
                 "launches_timed": len(gather_ms),
                 "share_of_step": sum(gather_ms) / max(elapsed_ms, 1e-9),
@@ -446,6 +453,7 @@ def main():
                        "n_patches": rad.n_patches, "visible_pairs": n_pairs,
                        "directed_pairs_kept": int(tables.src.numel()),
                        "tile_records": int(tables.n_records), "gather": args.gather,
+                       "record_window": int(tables.win_w),
                        "n_directions": n_dir, "n_bands": n_band, "n_samples": n_samples,
                        "reflection_orders": orders,
                        "exchanges_per_etc": x_per_step,

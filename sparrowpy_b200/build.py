@@ -21,6 +21,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
 SOURCES = [
     ("exchange.cu", []),
     ("exchange_tma.cu", []),
+    ("exchange_win.cu", []),
     ("bake.cu", ["--fmad=false"]),
 ]
 

@@ -34,7 +34,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .exchange import EnergyHistogram
+from .exchange import EnergyHistogram, gather_kind
 
 SHARD_ALIGN = 8
 
@@ -119,7 +119,13 @@ class ShardedExchange:
         t = self.t
         code = _lib.I32(t.dtype)
         st = _lib.stream_ptr()
-        if t.recs is not None and os.environ.get("SPB_GATHER", "tma") != "csr":
+        kind = gather_kind()
+        if t.win_recs is not None and kind != "csr":
+            _lib.call("spb_exchange_gather_window", prev, self.g, t.win_ptr, t.win_recs,
+                      self.cta_order(), t.n_patches, self.n_alloc, t.n_classes, t.n_dirs,
+                      t.n_bands, b_lo, b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld,
+                      self.pad, t.win_w, code, st)
+        elif t.recs is not None and kind != "csr":
             _lib.call("spb_exchange_gather_tiled", prev, self.g, t.ent_ptr, t.recs,
                       self.cta_order(), t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
                       b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad, code, st)
@@ -137,7 +143,8 @@ class ShardedExchange:
             n_r = 8
             n_blocks = -(-t.n_patches // n_r)
             jb_lo, jb_hi = self.j_lo // n_r, -(-self.j_hi // n_r)
-            counts = (t.ent_ptr[1:] - t.ent_ptr[:-1]).view(t.n_classes, n_blocks)
+            ptr = t.tile_ptr
+            counts = (ptr[1:] - ptr[:-1]).view(t.n_classes, n_blocks)
             local = counts[:, jb_lo:jb_hi].reshape(-1)
             self._cta_order = torch.argsort(local, descending=True, stable=True).to(
                 torch.int32).contiguous()

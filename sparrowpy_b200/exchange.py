@@ -35,6 +35,14 @@ class PairTables:
     n_records: int = 0
     rank: torch.Tensor = None      # (n_user,) int64 caller's patch id -> internal index
     n_user: int = 0                # caller's patch count (n_patches is the internal one)
+    win_ptr: torch.Tensor = None   # (C*ceil(N/R) + 1,) int64  window records (SPB_GATHER=win)
+    win_recs: torch.Tensor = None  # (n_records, 80) uint8
+    win_w: int = 0                 # delay window of the records (4 or 10 bins)
+
+    @property
+    def tile_ptr(self):
+        """Record offsets of whichever tiled gather these tables were built for."""
+        return self.win_ptr if self.win_recs is not None else self.ent_ptr
 
     def tiled(self, n_sources):
         """Tables for a batch of ``n_sources`` sources: a source is one more group of
@@ -73,8 +81,20 @@ def directed_pairs(pairs, ff_pairs, areas):
     return sender, receiver, ff
 
 
+def gather_kind(code=None):
+    """Stage-1 kernel selected by ``SPB_GATHER``: ``tma`` (default; bucket records,
+    exchange_tma.cu), ``win`` (register-window records, exchange_win.cu; FP64 only,
+    FP32 tables fall back to ``tma``) or ``csr`` (cross-check kernel)."""
+    kind = os.environ.get("SPB_GATHER", "tma")
+    if kind not in ("tma", "win", "csr"):
+        raise ValueError(f"SPB_GATHER={kind!r}: use tma, win or csr")
+    if kind == "win" and code is not None and code != _lib.F64:
+        kind = "tma"
+    return kind
+
+
 def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches,
-                      n_samples, dtype, rank=None, n_internal=None):
+                      n_samples, dtype, rank=None, n_internal=None, gather=None):
     """Sort directed pairs into segments (class, receiver) and drop pairs whose
     delay is >= n_samples (they contribute nothing, RadiosityFast.py:1137-1140).
 
@@ -107,11 +127,19 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     seg_ptr[1:] = torch.cumsum(counts, 0)
     src = (sender[order] * n_dirs + out_dir[order].long()).to(torch.int32)
     max_delay = int(delay.max().item()) if delay.numel() else 0
-    ent_ptr, recs = build_tile_records(sender, receiver, ff, delay, out_dir, cls, n_patches,
-                                       n_dirs, n_classes, code)
+    gather = gather or gather_kind(code)
+    ent_ptr = recs = win_ptr = win_recs = None
+    win_w = 0
+    if gather == "win" and code == _lib.F64:
+        win_ptr, win_recs, win_w = build_window_records(
+            sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs, n_classes, code)
+    else:
+        ent_ptr, recs = build_tile_records(sender, receiver, ff, delay, out_dir, cls,
+                                           n_patches, n_dirs, n_classes, code)
     return PairTables(
-        rank=rank, n_user=n_user,
-        ent_ptr=ent_ptr, recs=recs, n_records=int(recs.shape[0]),
+        rank=rank, n_user=n_user, win_ptr=win_ptr, win_recs=win_recs, win_w=win_w,
+        ent_ptr=ent_ptr, recs=recs,
+        n_records=int((recs if recs is not None else win_recs).shape[0]),
         seg_ptr=seg_ptr.contiguous(), src=src.contiguous(),
         wgt=ff[order].to(tdt).contiguous(),
         dly=delay[order].to(torch.int32).contiguous(),
@@ -189,6 +217,98 @@ def build_tile_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_d
     return ent_ptr.contiguous(), recs
 
 
+def window_geometry(code):
+    """(receivers per tile, widest delay window, record bytes) of the register-window
+    gather kernel (csrc/exchange_win.cu)."""
+    import ctypes
+    lib = _lib.load()
+    r, q, nbytes = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = lib.spb_window_geometry(ctypes.c_int(code), ctypes.byref(r), ctypes.byref(q),
+                                 ctypes.byref(nbytes))
+    if rc != 0:
+        raise _lib.SparrowB200Error(lib.spb_last_error().decode())
+    return r.value, q.value, nbytes.value
+
+
+WINDOW_CHOICES = (4, 10)     # instantiations of k_gather_win
+
+
+def _window_cover(delay_sorted, group, pos, n_groups, n_r, width):
+    """Greedy cover of every group's sorted delays by windows [base, base + width],
+    base even.  Returns (starts_new_record (bool), base per entry)."""
+    dev = delay_sorted.device
+    base = torch.zeros(n_groups, dtype=torch.int64, device=dev)
+    start = torch.zeros(delay_sorted.numel(), dtype=torch.bool, device=dev)
+    ebase = torch.zeros(delay_sorted.numel(), dtype=torch.int64, device=dev)
+    for p in range(n_r):
+        idx = torch.nonzero(pos == p).reshape(-1)
+        if idx.numel() == 0:
+            break
+        gp, dp = group[idx], delay_sorted[idx]
+        new = dp > base[gp] + width if p else torch.ones_like(dp, dtype=torch.bool)
+        base[gp[new]] = dp[new] & ~1
+        start[idx] = new
+        ebase[idx] = base[gp]
+    return start, ebase
+
+
+def build_window_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs,
+                         n_classes, code, width=None):
+    """Records of the register-window gather (csrc/exchange_win.cu).
+
+    A tile is R neighbouring receivers of one class.  The directed pairs of one
+    (tile, sender row) are covered greedily, in order of delay, by windows
+    ``[dbase, dbase + W]`` with ``dbase`` even; each window is one record
+    ``{w[R] f64, rel[R] u8 (delay - dbase, 255 = no pair), src i32, dbase i32}``.
+    ``W`` is the narrowest instantiated window that costs at most 2 % more records than
+    the widest one.  Pure index bookkeeping (sort / cumsum / scatter).
+    Returns ``(ent_ptr, recs, W)``.
+    """
+    n_r, max_w, rec_bytes = window_geometry(code)
+    tdt = _lib.torch_dtype(code)
+    dev = sender.device
+    n_blocks = -(-n_patches // n_r)
+    n_tiles = n_classes * n_blocks
+    if sender.numel() == 0:
+        return (torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev),
+                torch.zeros((0, rec_bytes), dtype=torch.uint8, device=dev), WINDOW_CHOICES[0])
+    n_rows = n_patches * n_dirs
+    delay = delay.long()
+    span = int(delay.max().item()) + 1
+    grp_key = (cls.long() * n_blocks + receiver.long() // n_r) * n_rows + (
+        sender.long() * n_dirs + out_dir.long())
+    order = torch.argsort(grp_key * span + delay)
+    gk, d = grp_key[order], delay[order]
+    first = torch.ones(gk.numel(), dtype=torch.bool, device=dev)
+    first[1:] = gk[1:] != gk[:-1]
+    group = torch.cumsum(first.long(), 0) - 1
+    n_groups = int(group[-1].item()) + 1
+    g_start = torch.nonzero(first).reshape(-1)
+    pos = torch.arange(gk.numel(), device=dev) - g_start[group]
+    assert int(pos.max().item()) < n_r, "more pairs than receiver slots in a group"
+    widths = [w for w in WINDOW_CHOICES if w <= max_w] if width is None else [int(width)]
+    covers = {w: _window_cover(d, group, pos, n_groups, n_r, w) for w in widths}
+    n_wide = int(covers[widths[-1]][0].sum().item())
+    width = next(w for w in widths if int(covers[w][0].sum().item()) <= 1.02 * n_wide)
+    start, ebase = covers[width]
+    rec = torch.cumsum(start.long(), 0) - 1
+    n_rec = int(rec[-1].item()) + 1
+    slot = (receiver.long() % n_r)[order]
+    w = torch.zeros((n_rec, n_r), dtype=tdt, device=dev)
+    w[rec, slot] = ff[order].to(tdt)
+    rel = torch.full((n_rec, n_r), 255, dtype=torch.uint8, device=dev)
+    rel[rec, slot] = (d - ebase).to(torch.uint8)
+    head = torch.nonzero(start).reshape(-1)                 # first entry of each record
+    meta = torch.stack([gk[head] % n_rows, ebase[head]], dim=1).to(torch.int32)
+    recs = torch.cat([w.view(torch.uint8), rel, meta.contiguous().view(torch.uint8)],
+                     dim=1).contiguous()
+    assert recs.shape[1] == rec_bytes, (recs.shape, rec_bytes)
+    counts = torch.bincount(gk[head] // n_rows, minlength=n_tiles)
+    ent_ptr = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
+    ent_ptr[1:] = torch.cumsum(counts, 0)
+    return ent_ptr.contiguous(), recs, width
+
+
 class EnergyHistogram:
     """(patch, direction, band, time) histogram in the padded-row device layout:
     ``data[(band * n_alloc + p) * D + dir, PAD + t]`` where ``p`` is the internal
@@ -257,6 +377,8 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
     """
     if e0.dim() == 4:
         return _energy_exchange_batch(tables, e0, delay0, n_samples, max_order)
+    if tables.win_recs is not None and gather_kind() != "csr":
+        return _energy_exchange_orders(tables, e0, delay0, n_samples, max_order)
     t = tables
     tdt = _lib.torch_dtype(t.dtype)
     device = e0.device
@@ -264,7 +386,7 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
     e0, delay0 = t.to_internal(e0), t.to_internal(delay0)
     e0 = e0.to(tdt).contiguous()
     delay0 = delay0.to(torch.int32).contiguous()
-    use_tiles = t.recs is not None and os.environ.get("SPB_GATHER", "tma") != "csr"
+    use_tiles = t.recs is not None and gather_kind() != "csr"
     _lib.call("spb_energy_exchange", e0, delay0, t.seg_ptr, t.src, t.wgt, t.dly,
               t.ent_ptr if use_tiles else None, t.recs if use_tiles else None, t.coef,
               t.n_patches, t.n_classes, t.n_dirs, t.n_bands, n_samples, ws.t_pad, ws.pad,
@@ -272,6 +394,16 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
               _lib.stream_ptr())
     return EnergyHistogram(ws.e_total, t.n_patches, t.n_dirs, t.n_bands, n_samples, ws.pad,
                            tables=t)
+
+
+def _energy_exchange_orders(tables, e0, delay0, n_samples, max_order):
+    """One source through the per-order driver (gather + mix launched from Python) --
+    the path of the register-window gather, which ``spb_energy_exchange`` does not
+    know about."""
+    from .distributed import ShardedExchange
+    sx = ShardedExchange(tables, n_samples, e0.device, need_orders=max_order >= 1)
+    sx.init(e0, delay0)
+    return sx.run(max(0, int(max_order)))
 
 
 def _energy_exchange_batch(tables, e0, delay0, n_samples, max_order):

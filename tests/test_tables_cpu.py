@@ -122,3 +122,72 @@ def test_compact_order_is_a_balanced_numbering():
         if len(m) > 1:
             ext.append(np.ptp(cen[m], axis=0).max())
     assert np.mean(ext) <= 3.0 + 1e-9        # 2 x 4 patches of 1 m: extent <= 3 m
+
+
+def decode_window_records(ent_ptr, recs, width, n_patches, n_r=8):
+    """(class, receiver, src_row, delay, weight) tuples encoded in the window records."""
+    recs, ent = recs.numpy(), ent_ptr.numpy()
+    n_blocks = -(-n_patches // n_r)
+    out = []
+    for tile in range(len(ent) - 1):
+        c, jb = divmod(tile, n_blocks)
+        prev = None
+        for e in range(ent[tile], ent[tile + 1]):
+            raw = recs[e]
+            w = raw[:64].view(np.float64)
+            rel = raw[64:72]
+            src, dbase = (int(x) for x in raw[72:].view(np.int32))
+            assert dbase % 2 == 0 and dbase >= 0
+            assert (src, dbase) > prev if prev is not None else True     # sorted, no duplicates
+            prev = (src, dbase)
+            used = rel != 255
+            assert used.any() and (rel[used] <= width).all() and (w[~used] == 0).all()
+            for s in np.nonzero(used)[0]:
+                out.append((c, jb * n_r + int(s), src, dbase + int(rel[s]), float(w[s])))
+    return sorted(out)
+
+
+@pytest.mark.parametrize("width", [None, 4, 10])
+def test_window_records_encode_the_same_pairs(width):
+    sender, receiver, ff, delay, out_dir, cls, coef, n, t_len = random_pairs(3)
+    keep = delay < t_len
+    args = [x[keep] for x in (sender, receiver, ff, delay, out_dir, cls)]
+    ent_ptr, recs, w = exchange.build_window_records(*args, n, 3, 4, _lib.F64, width=width)
+    assert w in exchange.WINDOW_CHOICES and (width is None or w == width)
+    want = sorted((int(c), int(r), int(s) * 3 + int(o), int(dl), float(x))
+                  for s, r, x, dl, o, c in zip(*args))
+    assert decode_window_records(ent_ptr, recs, w, n) == want
+
+
+def test_window_records_merge_neighbouring_delays():
+    """8 receivers of one tile seeing the same sender row with delays inside one window
+    become a single record; a delay outside it starts a second one."""
+    n, d = 16, 1
+    receiver = torch.arange(8)
+    sender = torch.full((8,), 12)
+    ff = torch.arange(1, 9, dtype=torch.float64)
+    delay = torch.tensor([41, 40, 43, 47, 50, 45, 44, 61])
+    zeros = torch.zeros(8, dtype=torch.int64)
+    ent_ptr, recs, w = exchange.build_window_records(sender, receiver, ff, delay, zeros, zeros,
+                                                     n, d, 1, _lib.F64, width=10)
+    assert ent_ptr.tolist() == [0, 2, 2] and recs.shape == (2, 80)
+    raw = recs.numpy()
+    assert raw[0, 64:72].tolist() == [1, 0, 3, 7, 10, 5, 4, 255]
+    assert raw[0, 72:].view(np.int32).tolist() == [12, 40]
+    assert raw[1, 64:72].tolist() == [255] * 7 + [1] and raw[1, 72:].view(np.int32).tolist() == [12, 60]
+    assert raw[1, :64].view(np.float64).tolist() == [0.0] * 7 + [8.0]
+
+
+def test_window_swizzle_is_conflict_free():
+    """The shared-memory layout of k_gather_win: a lane reads 16-byte chunks
+    v = 128*warp + 4*lane + q (q = window chunk); with chunk bits 0-1 ^= bits 3-4 the 8
+    lanes of every quarter warp (one LDS.128 wavefront) fall into 8 different 16-byte
+    bank groups for every q, and the map is a permutation inside each 512-byte block."""
+    swz = lambda v: v ^ ((v >> 3) & 3)    # noqa: E731
+    assert sorted(swz(v) for v in range(64)) == list(range(64))
+    for warp in range(8):
+        for q in range(9):
+            for quarter in range(4):
+                groups = {swz(128 * warp + 4 * lane + q) % 8
+                          for lane in range(8 * quarter, 8 * quarter + 8)}
+                assert len(groups) == 8

@@ -311,7 +311,8 @@ def main():
         if t.win_recs is not None and args.gather == "win":
             _lib.call("spb_exchange_gather_window", prev, sx.g, t.win_ptr, t.win_recs,
                       sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands,
-                      b_lo, b_hi, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, t.win_w, c32, sp)
+                      b_lo, b_hi, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad,
+                      exchange.window_arg(t), c32, sp)
         elif args.gather != "csr":
             _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
                       sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,

@@ -31,9 +31,7 @@ namespace spb {
 namespace win {
 
 constexpr int kR = 8;                  // receivers per tile
-constexpr int kLaneT = 8;              // consecutive time bins per lane
-constexpr int kWarpT = 32 * kLaneT;    // 256 bins per consumer warp
-constexpr int kMaxWarps = 8;           // consumer warps per CTA
+constexpr int kCtaT = 2048;            // most time bins one CTA covers
 constexpr int kMaxW = 10;              // widest delay window of a record
 constexpr int kStages = 12;
 constexpr int kRecPad = 128;           // bytes reserved for the staged record
@@ -82,17 +80,21 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
                  : "memory");
 }
 
-// 16-byte chunk index -> swizzled chunk index
-__device__ __forceinline__ int swz(int v) { return v ^ ((v >> 3) & 3); }
+// 16-byte chunk index -> swizzled chunk index.  LT = 8 bins per lane: lane stride 4
+// chunks, bits 0-1 ^= bits 3-4; LT = 4: lane stride 2 chunks, bit 0 ^= bit 3.
+template <int LT>
+__device__ __forceinline__ int swz(int v) {
+    return v ^ ((v >> 3) & (LT == 8 ? 3 : 1));
+}
 
 // acc[k] += w * win[k + W - rel]   (rel warp-uniform)
-template <int W>
-__device__ __forceinline__ void accumulate(double (&acc)[kLaneT], double w,
-                                           const double (&win)[kLaneT + W], unsigned rel) {
+template <int W, int LT>
+__device__ __forceinline__ void accumulate(double (&acc)[LT], double w,
+                                           const double (&win)[LT + W], unsigned rel) {
 #define SPB_WIN_CASE(R)                                                     \
     case R:                                                                 \
         if constexpr (R <= W) {                                             \
-            _Pragma("unroll") for (int k = 0; k < kLaneT; ++k)              \
+            _Pragma("unroll") for (int k = 0; k < LT; ++k)                  \
                 acc[k] = fma(w, win[k + (W - R < 0 ? 0 : W - R)], acc[k]);  \
         }                                                                   \
         break;
@@ -123,8 +125,8 @@ __device__ __forceinline__ void accumulate(double (&acc)[kLaneT], double w,
 // released it, so the warps are only loosely coupled.
 constexpr int kAhead = 8;              // prefetch distance in records (< kStages)
 
-template <int W>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+template <int W, int LT>
+__global__ void __launch_bounds__(kCtaT / LT, 1)
 k_gather_win(const double *__restrict__ e_prev, double *__restrict__ g,
              const int64_t *__restrict__ ent_ptr, const WinRecord *__restrict__ recs,
              int64_t n_patches, int64_t n_alloc, int64_t n_blocks, int64_t n_dirs, int64_t b_lo,
@@ -147,6 +149,7 @@ k_gather_win(const double *__restrict__ e_prev, double *__restrict__ g,
     const int64_t e0 = ent_ptr[tile];
     const int n_rec = (int)(ent_ptr[tile + 1] - e0);
     if (n_rec == 0) return;                       // no pairs: rows are never read
+    constexpr int kWarpT = 32 * LT;               // time bins per warp
     const int64_t t0 = (int64_t)blockIdx.y * n_warps * kWarpT;
     const int n_active = (int)min((int64_t)n_warps, (t_pad - t0) / kWarpT);
 
@@ -167,7 +170,7 @@ k_gather_win(const double *__restrict__ e_prev, double *__restrict__ g,
     const int n_chunks = (n_active * kWarpT + W) / 2;            // 16-byte chunks per row
     const int n_mine = (n_chunks - tid + n_thr - 1) / n_thr;     // chunks tid, tid + n_thr, ...
     const uint32_t smem0 = smem_u32(smem_raw);
-    const uint32_t my_dst = (uint32_t)(swz(tid) << 4);   // swz(tid + 32 m) = swz(tid) + 32 m
+    const uint32_t my_dst = (uint32_t)(swz<LT>(tid) << 4);   // swz(tid + 32 m) = swz(tid) + 32 m
     const WinRecord *rec0 = recs + e0;
     // src / dbase of the records: read 32 at a time (lane l holds record base + l),
     // the next batch one batch ahead of its use
@@ -204,22 +207,23 @@ k_gather_win(const double *__restrict__ e_prev, double *__restrict__ g,
     for (int p = 0; p < kAhead && p < n_rec; ++p) issue();
 
     // ---- compute side: 256 time bins (8 per lane) of all 8 receivers ----
-    double acc[kR][kLaneT];
+    double acc[kR][LT];
 #pragma unroll
     for (int s = 0; s < kR; ++s)
 #pragma unroll
-        for (int k = 0; k < kLaneT; ++k) acc[s][k] = 0.0;
-    const int vbase = warp * (kWarpT / 2) + lane * (kLaneT / 2);   // first chunk of my window
+        for (int k = 0; k < LT; ++k) acc[s][k] = 0.0;
+    const int vbase = warp * (kWarpT / 2) + lane * (LT / 2);   // first chunk of my window
     int stage = 0;
     uint32_t phase = 0;
     for (int r = 0; r < n_rec; ++r) {
         if (p_rec < n_rec) issue();
         mbar_wait(&full[stage], phase);
         const unsigned char *sw = smem_raw + (size_t)stage * stage_stride;
-        double win[kLaneT + W];
+        double win[LT + W];
 #pragma unroll
-        for (int q = 0; q < (kLaneT + W) / 2; ++q) {
-            const double2 x = *reinterpret_cast<const double2 *>(sw + (swz(vbase + q) << 4));
+        for (int q = 0; q < (LT + W) / 2; ++q) {
+            const double2 x =
+                *reinterpret_cast<const double2 *>(sw + (swz<LT>(vbase + q) << 4));
             win[2 * q] = x.x;
             win[2 * q + 1] = x.y;
         }
@@ -227,7 +231,7 @@ k_gather_win(const double *__restrict__ e_prev, double *__restrict__ g,
         const uint64_t rel = *reinterpret_cast<const uint64_t *>(rec->rel);
 #pragma unroll
         for (int s = 0; s < kR; ++s)
-            accumulate<W>(acc[s], rec->w[s], win, (unsigned)((rel >> (8 * s)) & 0xffu));
+            accumulate<W, LT>(acc[s], rec->w[s], win, (unsigned)((rel >> (8 * s)) & 0xffu));
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -238,15 +242,15 @@ k_gather_win(const double *__restrict__ e_prev, double *__restrict__ g,
         if (j < n_patches) {
             double2 *out = reinterpret_cast<double2 *>(
                 g + ((b * n_classes + c) * n_patches + j) * ld + pad + t0 + warp * kWarpT +
-                lane * kLaneT);
+                lane * LT);
 #pragma unroll
-            for (int k = 0; k < kLaneT / 2; ++k)
+            for (int k = 0; k < LT / 2; ++k)
                 out[k] = make_double2(acc[s][2 * k], acc[s][2 * k + 1]);
         }
     }
 }
 
-template <int W>
+template <int W, int LT>
 int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRecord *recs,
            const int32_t *cta_order, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
            int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi, int64_t t_pad,
@@ -260,6 +264,8 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
     // time slices: as few CTAs along time as possible (a CTA stages each sender row
     // once for all its warps), equal shares; small grids use narrower CTAs so that the
     // machine is filled at least once
+    constexpr int kWarpT = 32 * LT;
+    constexpr int kMaxWarps = kCtaT / kWarpT;
     const int64_t m = t_pad / kWarpT;
     int64_t n_y = ceil_div(m, (int64_t)kMaxWarps);
     int n_warps = (int)ceil_div(m, n_y);
@@ -270,10 +276,10 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
     const int win_bytes = (n_warps * kWarpT + W) * (int)sizeof(double);
     const int win_stride = (win_bytes + 511) / 512 * 512;
     const size_t smem = (size_t)(win_stride + kRecPad) * kStages + 2 * kStages * sizeof(uint64_t);
-    SPB_CUDA(cudaFuncSetAttribute(k_gather_win<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPB_CUDA(cudaFuncSetAttribute(k_gather_win<W, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     dim3 grid((unsigned)n_cta, (unsigned)n_y);
-    k_gather_win<W><<<grid, n_warps * 32, smem, st>>>(
+    k_gather_win<W, LT><<<grid, n_warps * 32, smem, st>>>(
         e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_blocks, n_dirs, b_lo, jb_lo, n_jb,
         n_classes, t_pad, ld, pad, n_warps, win_stride, cta_order);
     return check_launch("k_gather_win");
@@ -308,17 +314,20 @@ int spb_exchange_gather_window(const void *e_prev, void *g, const int64_t *ent_p
     SPB_REQUIRE(n_alloc >= n_patches, "n_alloc < n_patches");
     SPB_REQUIRE(j_lo == j_hi || j_lo % win::kR == 0,
                 "j_lo must be a multiple of the receiver tile (8)");
-    SPB_REQUIRE(t_pad % win::kWarpT == 0 && ld == pad + t_pad, "layout (use spb_exchange_layout)");
+    SPB_REQUIRE(t_pad % 256 == 0 && ld == pad + t_pad, "layout (use spb_exchange_layout)");
     SPB_REQUIRE(pad % 32 == 0 && pad >= 64, "pad (use spb_exchange_layout)");
     cudaStream_t st = (cudaStream_t)stream;
     const double *ep = (const double *)e_prev;
     const win::WinRecord *r = (const win::WinRecord *)recs;
-    if (window == 4)
-        return win::launch<4>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc, n_classes,
-                              n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
-    if (window == 10)
-        return win::launch<10>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
-                               n_classes, n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
+#define SPB_WIN_LAUNCH(W_, LT_)                                                              \
+    return win::launch<W_, LT_>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,  \
+                                n_classes, n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st)
+    // window + 100: tuning variant with 4 bins per lane and up to 16 warps per CTA
+    if (window == 4) SPB_WIN_LAUNCH(4, 8);
+    if (window == 10) SPB_WIN_LAUNCH(10, 8);
+    if (window == 104) SPB_WIN_LAUNCH(4, 4);
+    if (window == 110) SPB_WIN_LAUNCH(10, 4);
+#undef SPB_WIN_LAUNCH
     return fail(-1, "invalid argument", "window must be 4 or 10");
 }
 

@@ -34,7 +34,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .exchange import EnergyHistogram, gather_kind
+from .exchange import EnergyHistogram, gather_kind, window_arg
 
 SHARD_ALIGN = 8
 
@@ -124,7 +124,7 @@ class ShardedExchange:
             _lib.call("spb_exchange_gather_window", prev, self.g, t.win_ptr, t.win_recs,
                       self.cta_order(), t.n_patches, self.n_alloc, t.n_classes, t.n_dirs,
                       t.n_bands, b_lo, b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld,
-                      self.pad, t.win_w, code, st)
+                      self.pad, window_arg(t), code, st)
         elif t.recs is not None and kind != "csr":
             _lib.call("spb_exchange_gather_tiled", prev, self.g, t.ent_ptr, t.recs,
                       self.cta_order(), t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,

@@ -93,6 +93,12 @@ def gather_kind(code=None):
     return kind
 
 
+def window_arg(tables):
+    """``window`` argument of spb_exchange_gather_window: the record window, +100 for the
+    tuning variant with 4 instead of 8 time bins per lane (``SPB_WIN_LANE_T=4``)."""
+    return tables.win_w + (100 if os.environ.get("SPB_WIN_LANE_T", "8") == "4" else 0)
+
+
 def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches,
                       n_samples, dtype, rank=None, n_internal=None, gather=None):
     """Sort directed pairs into segments (class, receiver) and drop pairs whose

@@ -191,3 +191,12 @@ def test_window_swizzle_is_conflict_free():
                 groups = {swz(128 * warp + 4 * lane + q) % 8
                           for lane in range(8 * quarter, 8 * quarter + 8)}
                 assert len(groups) == 8
+    # variant with 4 bins per lane: lane stride 2 chunks, bit 0 ^= bit 3
+    swz4 = lambda v: v ^ ((v >> 3) & 1)   # noqa: E731
+    assert sorted(swz4(v) for v in range(64)) == list(range(64))
+    for warp in range(16):
+        for q in range(7):
+            for quarter in range(4):
+                groups = {swz4(64 * warp + 2 * lane + q) % 8
+                          for lane in range(8 * quarter, 8 * quarter + 8)}
+                assert len(groups) == 8

@@ -34,7 +34,8 @@ def ragged(seed, n, d, c, m, max_delay, spread, dev):
 @pytest.mark.parametrize("t_len,spread,width", [
     (300, 3, 4), (300, 9, 10), (300, 25, 10), (1000, 9, 4), (1200, 6, 10), (2000, 9, 10),
     (2300, 10, 10), (5000, 4, 4)])
-def test_window_gather_equals_csr_gather(t_len, spread, width, monkeypatch):
+@pytest.mark.parametrize("lane_t", [8, 4])
+def test_window_gather_equals_csr_gather(t_len, spread, width, lane_t, monkeypatch):
     from sparrowpy_b200 import _lib, exchange
     monkeypatch.setenv("SPB_GATHER", "win")
     dev = torch.device("cuda:0")
@@ -58,10 +59,13 @@ def test_window_gather_equals_csr_gather(t_len, spread, width, monkeypatch):
     g1 = torch.zeros((b * c * n, ld), dtype=torch.float64, device=dev)
     g2 = torch.zeros_like(g1)
     st, code = _lib.stream_ptr(), _lib.I32(tables.dtype)
+    monkeypatch.setenv("SPB_WIN_LANE_T", str(lane_t))
+    win_arg = exchange.window_arg(tables)
+    assert win_arg == width + (100 if lane_t == 4 else 0)
     _lib.call("spb_exchange_gather", prev, g1, tables.seg_ptr, tables.src, tables.wgt,
               tables.dly, n, n, c, d, b, 0, b, 0, n, t_pad, ld, pad, code, st)
     _lib.call("spb_exchange_gather_window", prev, g2, tables.win_ptr, tables.win_recs, None, n,
-              n, c, d, b, 0, b, 0, n, t_pad, ld, pad, tables.win_w, code, st)
+              n, c, d, b, 0, b, 0, n, t_pad, ld, pad, win_arg, code, st)
     torch.cuda.synchronize()
     a, bb = g1[:, pad:pad + t_len], g2[:, pad:pad + t_len]
     assert a.abs().max() > 0
@@ -72,10 +76,10 @@ def test_window_gather_equals_csr_gather(t_len, spread, width, monkeypatch):
     order = torch.arange(n_tiles - 1, -1, -1, dtype=torch.int32, device=dev)
     g3 = torch.zeros_like(g1)
     _lib.call("spb_exchange_gather_window", prev, g3, tables.win_ptr, tables.win_recs, order, n,
-              n, c, d, b, 0, b, 0, n, t_pad, ld, pad, tables.win_w, code, st)
+              n, c, d, b, 0, b, 0, n, t_pad, ld, pad, win_arg, code, st)
     g4 = torch.zeros_like(g1)
     _lib.call("spb_exchange_gather_window", prev, g4, tables.win_ptr, tables.win_recs, None, n,
-              n, c, d, b, 1, 2, 16, 40, t_pad, ld, pad, tables.win_w, code, st)
+              n, c, d, b, 1, 2, 16, 40, t_pad, ld, pad, win_arg, code, st)
     torch.cuda.synchronize()
     assert torch.equal(g2, g3)
     g4v, g2v = g4.view(b, c, n, ld), g2.view(b, c, n, ld)

@@ -26,6 +26,7 @@
 // dbase even, rel = delay - dbase in [0, W], rel = 255 for an empty slot
 // (exchange.build_window_records).
 #include "common.cuh"
+#include "win_dispatch.cuh"
 
 namespace spb {
 namespace win {
@@ -250,7 +251,131 @@ k_gather_win(const double *__restrict__ e_prev, double *__restrict__ g,
     }
 }
 
-template <int W, int LT>
+// ---------------------------------------------------------------------------------
+// Variant 2 (window + 200, SPB_WIN_VARIANT=2): same records, same staging layout, two
+// changes aimed at what the profile of variant 1 shows (profiles/r01_k_gather_win_c4_f64.txt:
+// 316 instructions per (warp, record) for 58 DFMAs, branches = half of all stall samples):
+//   * the row of record r is copied by ONE warp, warp r mod n_warps, with an unrolled
+//     run of LDGSTS at immediate offsets; the fixed costs (barrier wait, header, address
+//     arithmetic, loop control) are paid once per n_warps records and warp instead of
+//     once per record and warp.  full[s] counts the 32 lanes of the copying warp.
+//   * the per-(record, receiver) dispatch is one indirect branch through a jump table
+//     (win_dispatch.cuh, `brx.idx`) instead of a compare tree.
+// ---------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kCtaT / 8, 1)
+k_gather_win2(const double *__restrict__ e_prev, double *__restrict__ g,
+              const int64_t *__restrict__ ent_ptr, const WinRecord *__restrict__ recs,
+              int64_t n_patches, int64_t n_alloc, int64_t n_blocks, int64_t n_dirs,
+              int64_t b_lo, int64_t jb_lo, int64_t n_jb, int64_t n_classes, int64_t t_pad,
+              int64_t ld, int64_t pad, int n_warps, int win_stride,
+              const int32_t *__restrict__ cta_order) {
+    constexpr int LT = 8;
+    constexpr int kWarpT = 32 * LT;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int stage_stride = win_stride + kRecPad;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stage_stride * kStages);
+    uint64_t *empty = full + kStages;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t n_local = n_classes * n_jb;
+    const int64_t b = b_lo + blockIdx.x / n_local;
+    const int64_t pos = blockIdx.x % n_local;
+    const int64_t loc = cta_order ? cta_order[pos] : pos;     // longest tiles first
+    const int64_t c = loc / n_jb;
+    const int64_t jb = jb_lo + (loc - c * n_jb);
+    const int64_t tile = c * n_blocks + jb;
+    const int64_t e0 = ent_ptr[tile];
+    const int n_rec = (int)(ent_ptr[tile + 1] - e0);
+    if (n_rec == 0) return;
+    const int64_t t0 = (int64_t)blockIdx.y * n_warps * kWarpT;
+    const int n_active = (int)min((int64_t)n_warps, (t_pad - t0) / kWarpT);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 32);              // the 32 lanes of the copying warp
+            mbar_init(&empty[s], n_active);       // one release per warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp >= n_active) return;
+
+    // ---- copy duty: rows of the records r = warp, warp + n_active, ... ----
+    const double *band_base = e_prev + b * n_alloc * n_dirs * ld + pad + t0 - W;
+    const int n_chunks = (n_active * kWarpT + W) / 2;            // 16-byte chunks per row
+    const int n_full = n_chunks >> 5, n_tail = n_chunks & 31;
+    const uint32_t smem0 = smem_u32(smem_raw);
+    const uint32_t lane_dst = (uint32_t)(swz<LT>(lane) << 4);    // swz(lane + 32 q) = swz(lane) + 32 q
+    const WinRecord *rec0 = recs + e0;
+    int duty = warp;                              // next record whose row this warp copies
+    int32_t h_src = 0, h_db = 0;                  // its header, loaded one duty ahead
+    if (duty < n_rec) { h_src = rec0[duty].src; h_db = rec0[duty].dbase; }
+    auto copy_row = [&]() {
+        const int stage = duty % kStages;
+        const uint32_t parity = (uint32_t)((duty / kStages) & 1);
+        mbar_wait(&empty[stage], parity ^ 1);
+        const char *src =
+            reinterpret_cast<const char *>(band_base + (int64_t)h_src * ld - h_db) + (lane << 4);
+        const uint32_t dst = smem0 + (uint32_t)stage * (uint32_t)stage_stride;
+#pragma unroll 8
+        for (int q = 0; q < n_full; ++q) cp_async16(dst + lane_dst + (q << 9), src + (q << 9));
+        if (lane < n_tail) cp_async16(dst + lane_dst + (n_full << 9), src + (n_full << 9));
+        if (lane < (int)(sizeof(WinRecord) / 16))
+            cp_async16(dst + (uint32_t)win_stride + (lane << 4),
+                       reinterpret_cast<const char *>(rec0 + duty) + (lane << 4));
+        cp_async_arrive(&full[stage]);
+        duty += n_active;
+        if (duty < n_rec) { h_src = rec0[duty].src; h_db = rec0[duty].dbase; }
+    };
+    while (duty < n_rec && duty < kAhead) copy_row();
+
+    // ---- compute: 256 time bins (8 per lane) of all 8 receivers ----
+    double acc[kR][LT];
+#pragma unroll
+    for (int s = 0; s < kR; ++s)
+#pragma unroll
+        for (int k = 0; k < LT; ++k) acc[s][k] = 0.0;
+    const int vbase = warp * (kWarpT / 2) + lane * (LT / 2);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int r = 0; r < n_rec; ++r) {
+        if (duty < n_rec && duty <= r + kAhead) copy_row();
+        mbar_wait(&full[stage], phase);
+        const unsigned char *sw = smem_raw + (size_t)stage * stage_stride;
+        double win[LT + W];
+#pragma unroll
+        for (int q = 0; q < (LT + W) / 2; ++q) {
+            const double2 x =
+                *reinterpret_cast<const double2 *>(sw + (swz<LT>(vbase + q) << 4));
+            win[2 * q] = x.x;
+            win[2 * q + 1] = x.y;
+        }
+        const WinRecord *rec = reinterpret_cast<const WinRecord *>(sw + win_stride);
+        const uint64_t rel = *reinterpret_cast<const uint64_t *>(rec->rel);
+#pragma unroll
+        for (int s = 0; s < kR; ++s)
+            accumulate_brx<W, LT>(acc[s], rec->w[s], win, (unsigned)((rel >> (8 * s)) & 0xffu));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+#pragma unroll
+    for (int s = 0; s < kR; ++s) {
+        const int64_t j = jb * kR + s;
+        if (j < n_patches) {
+            double2 *out = reinterpret_cast<double2 *>(
+                g + ((b * n_classes + c) * n_patches + j) * ld + pad + t0 + warp * kWarpT +
+                lane * LT);
+#pragma unroll
+            for (int k = 0; k < LT / 2; ++k)
+                out[k] = make_double2(acc[s][2 * k], acc[s][2 * k + 1]);
+        }
+    }
+}
+
+template <int W, int LT, int VARIANT = 1>
 int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRecord *recs,
            const int32_t *cta_order, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
            int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t j_lo, int64_t j_hi, int64_t t_pad,
@@ -276,13 +401,23 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
     const int win_bytes = (n_warps * kWarpT + W) * (int)sizeof(double);
     const int win_stride = (win_bytes + 511) / 512 * 512;
     const size_t smem = (size_t)(win_stride + kRecPad) * kStages + 2 * kStages * sizeof(uint64_t);
-    SPB_CUDA(cudaFuncSetAttribute(k_gather_win<W, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
     dim3 grid((unsigned)n_cta, (unsigned)n_y);
-    k_gather_win<W, LT><<<grid, n_warps * 32, smem, st>>>(
-        e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_blocks, n_dirs, b_lo, jb_lo, n_jb,
-        n_classes, t_pad, ld, pad, n_warps, win_stride, cta_order);
-    return check_launch("k_gather_win");
+    if constexpr (VARIANT == 2) {
+        static_assert(LT == 8, "variant 2 has 8 bins per lane");
+        SPB_CUDA(cudaFuncSetAttribute(k_gather_win2<W>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gather_win2<W><<<grid, n_warps * 32, smem, st>>>(
+            e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_blocks, n_dirs, b_lo, jb_lo, n_jb,
+            n_classes, t_pad, ld, pad, n_warps, win_stride, cta_order);
+        return check_launch("k_gather_win2");
+    } else {
+        SPB_CUDA(cudaFuncSetAttribute(k_gather_win<W, LT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gather_win<W, LT><<<grid, n_warps * 32, smem, st>>>(
+            e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_blocks, n_dirs, b_lo, jb_lo, n_jb,
+            n_classes, t_pad, ld, pad, n_warps, win_stride, cta_order);
+        return check_launch("k_gather_win");
+    }
 }
 
 }  // namespace win
@@ -319,14 +454,18 @@ int spb_exchange_gather_window(const void *e_prev, void *g, const int64_t *ent_p
     cudaStream_t st = (cudaStream_t)stream;
     const double *ep = (const double *)e_prev;
     const win::WinRecord *r = (const win::WinRecord *)recs;
-#define SPB_WIN_LAUNCH(W_, LT_)                                                              \
-    return win::launch<W_, LT_>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,  \
-                                n_classes, n_dirs, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st)
+#define SPB_WIN_LAUNCH(W_, LT_, V_)                                                          \
+    return win::launch<W_, LT_, V_>(ep, (double *)g, ent_ptr, r, cta_order, n_patches,       \
+                                    n_alloc, n_classes, n_dirs, b_lo, b_hi, j_lo, j_hi,      \
+                                    t_pad, ld, pad, st)
     // window + 100: tuning variant with 4 bins per lane and up to 16 warps per CTA
-    if (window == 4) SPB_WIN_LAUNCH(4, 8);
-    if (window == 10) SPB_WIN_LAUNCH(10, 8);
-    if (window == 104) SPB_WIN_LAUNCH(4, 4);
-    if (window == 110) SPB_WIN_LAUNCH(10, 4);
+    // window + 200: variant 2 (row copied by one warp per record, jump-table dispatch)
+    if (window == 4) SPB_WIN_LAUNCH(4, 8, 1);
+    if (window == 10) SPB_WIN_LAUNCH(10, 8, 1);
+    if (window == 104) SPB_WIN_LAUNCH(4, 4, 1);
+    if (window == 110) SPB_WIN_LAUNCH(10, 4, 1);
+    if (window == 204) SPB_WIN_LAUNCH(4, 8, 2);
+    if (window == 210) SPB_WIN_LAUNCH(10, 8, 2);
 #undef SPB_WIN_LAUNCH
     return fail(-1, "invalid argument", "window must be 4 or 10");
 }

@@ -94,8 +94,12 @@ def gather_kind(code=None):
 
 
 def window_arg(tables):
-    """``window`` argument of spb_exchange_gather_window: the record window, +100 for the
-    tuning variant with 4 instead of 8 time bins per lane (``SPB_WIN_LANE_T=4``)."""
+    """``window`` argument of spb_exchange_gather_window: the record window, plus a
+    tuning variant selected by the environment -- +100: 4 instead of 8 time bins per
+    lane (``SPB_WIN_LANE_T=4``); +200: variant 2, row copied by one warp per record and
+    jump-table dispatch (``SPB_WIN_VARIANT=2``; compiled but not yet run on a GPU)."""
+    if os.environ.get("SPB_WIN_VARIANT", "1") == "2":
+        return tables.win_w + 200
     return tables.win_w + (100 if os.environ.get("SPB_WIN_LANE_T", "8") == "4" else 0)
 
 

@@ -57,8 +57,9 @@ class ShardedExchange:
     """
 
     def __init__(self, tables, n_samples, device, group=None, compute=None,
-                 layout=None, need_orders=True):
+                 layout=None, need_orders=True, gather_total=True):
         self.t = tables
+        self.gather_total = gather_total     # False: E_total stays sharded (own rows only)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -264,7 +265,7 @@ class ShardedExchange:
             for st in streams[1:]:
                 main.wait_stream(st)
             self._barrier()                      # all stores landed before buffers are reused
-            for b in range(nb):
+            for b in range(nb if self.gather_total else 0):
                 self._all_gather_band(self.e_total, b)
         elif not self.cuda:
             for _ in range(max_order):
@@ -272,7 +273,7 @@ class ShardedExchange:
                 for b in range(nb):
                     self._all_gather_band(cur, b)
                 prev, cur = cur, prev
-            for b in range(nb):
+            for b in range(nb if self.gather_total else 0):
                 self._all_gather_band(self.e_total, b)
         else:
             comp = torch.cuda.current_stream()
@@ -298,7 +299,108 @@ class ShardedExchange:
             for ev in ready:
                 if ev is not None:
                     comp.wait_event(ev)
-            for b in range(nb):
+            for b in range(nb if self.gather_total else 0):
                 self._all_gather_band(self.e_total, b)
         return EnergyHistogram(self.e_total, t.n_patches, t.n_dirs, t.n_bands,
                                self.n_samples, self.pad, n_alloc=self.n_alloc, tables=t)
+
+
+class ShardedHistogram:
+    """``sum_k E_k`` of a large scene, kept sharded: this rank holds the rows of its own
+    receiver patches only, ``data[(band * shard + (p - j_lo)) * D + dir, PAD + t]`` with
+    ``p`` the internal patch index.  Receiver collection sums the rank's patches and
+    all-reduces the (R, B, T) result -- the full histogram never exists anywhere."""
+
+    def __init__(self, data, tables, n_samples, pad, j_lo, j_hi, shard, group=None,
+                 collect=None):
+        self.data, self.tables = data, tables
+        self.n_samples, self.pad = n_samples, pad
+        self.j_lo, self.j_hi, self.shard = j_lo, j_hi, shard
+        self.group = group
+        self.collect = collect          # CPU stand-in for exchange.collect_mono (tests)
+
+    def local(self):
+        """The rank's rows as an EnergyHistogram over ``shard`` local patches."""
+        t = self.tables
+        return EnergyHistogram(self.data, self.shard, t.n_dirs, t.n_bands, self.n_samples,
+                               self.pad, n_alloc=self.shard)
+
+    def dense_local(self):
+        """(j_hi - j_lo, D, B, T): the rank's receivers in internal order."""
+        return self.local().dense()[:self.j_hi - self.j_lo]
+
+    def collect_mono(self, rdir, shift, scale):
+        """``collect_energy_receiver_mono`` over all ranks: rdir, shift (R, N) int32 and
+        scale (R, N, B) in the caller's patch numbering, as for exchange.collect_mono."""
+        from . import exchange
+        t = self.tables
+        own = slice(self.j_lo, self.j_lo + self.shard)
+
+        def mine(x):
+            x = t.to_internal(x, 1)
+            if x.shape[1] < self.j_lo + self.shard:          # last shard: pad with zeros
+                padn = self.j_lo + self.shard - x.shape[1]
+                x = torch.cat([x, x.new_zeros((x.shape[0], padn) + x.shape[2:])], 1)
+            return x[:, own].contiguous()
+
+        fn = self.collect or exchange.collect_mono
+        out = fn(self.local(), mine(rdir), mine(shift), mine(scale))
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(out, group=self.group)
+        return out
+
+
+class BandwiseExchange:
+    """Memory-bounded schedule for large scenes (BASELINE config 5: ~100 k patches,
+    16 directions, 8 bands).  Bands never mix (RadiosityFast.py:1137-1143 acts per band
+    and the BRDF coefficients carry the band index), so the recursion is run band block
+    by band block: the ping-pong buffers and the block's ``E_total`` exist for ONE block
+    at a time (the inner :class:`ShardedExchange`, re-used), and after a block only the
+    rows of this rank's receivers are kept.  Peak memory per rank is
+    ``3 * block * N * D * LD + B * N / world * D * LD`` elements instead of
+    ``3 * B * N * D * LD``."""
+
+    def __init__(self, tables, n_samples, device, band_block=1, group=None, compute=None,
+                 collect=None):
+        import dataclasses
+        self.t = tables
+        self.n_samples = n_samples
+        self.band_block = max(1, min(int(band_block), tables.n_bands))
+        self.group = group
+        self.collect = collect
+        view = dataclasses.replace(
+            tables, coef=tables.coef[:, :, :self.band_block].contiguous(),
+            n_bands=self.band_block)
+        self.sx = ShardedExchange(view, n_samples, device, group=group, compute=compute,
+                                  gather_total=False)
+        sx = self.sx
+        # rows this rank keeps per band: its shard (all shards are padded to the same
+        # size when world > 1), or simply every patch on a single GPU
+        self.own = sx.shard if sx.world > 1 else tables.n_patches
+        rows = tables.n_bands * self.own * tables.n_dirs
+        self.total = torch.zeros((rows, sx.ld), dtype=sx.e_total.dtype, device=device)
+
+    def _block_tables(self, b0, b1):
+        import dataclasses
+        return dataclasses.replace(self.t, coef=self.t.coef[:, :, b0:b1].contiguous(),
+                                   n_bands=b1 - b0)
+
+    def run(self, e0, delay0, max_order):
+        """e0 (N, D, B), delay0 (N,) in the caller's numbering -> ShardedHistogram."""
+        t, sx = self.t, self.sx
+        d, nb = t.n_dirs, t.n_bands
+        self.total.zero_()
+        for b0 in range(0, nb, self.band_block):
+            b1 = min(nb, b0 + self.band_block)
+            if b1 - b0 != sx.t.n_bands:
+                raise ValueError("n_bands must be a multiple of band_block")
+            sx.t = self._block_tables(b0, b1)
+            sx.init(e0[:, :, b0:b1].contiguous(), delay0)
+            sx.run(max_order)
+            for b in range(b0, b1):                  # keep the rank's rows of the block
+                r0 = b * self.own * d
+                src0 = ((b - b0) * sx.n_alloc + sx.j_lo) * d
+                self.total[r0:r0 + self.own * d].copy_(
+                    sx.e_total[src0:src0 + self.own * d])
+        return ShardedHistogram(self.total, t, self.n_samples, sx.pad, sx.j_lo, sx.j_hi,
+                                self.own, group=self.group, collect=self.collect)

@@ -104,7 +104,8 @@ def window_arg(tables):
 
 
 def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches,
-                      n_samples, dtype, rank=None, n_internal=None, gather=None):
+                      n_samples, dtype, rank=None, n_internal=None, gather=None,
+                      receiver_range=None):
     """Sort directed pairs into segments (class, receiver) and drop pairs whose
     delay is >= n_samples (they contribute nothing, RadiosityFast.py:1137-1140).
 
@@ -114,6 +115,12 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     numbering makes the 8 receivers of a tile close neighbours (more shared senders,
     directions and delay bins per record).  Histograms come back in the caller's
     numbering (EnergyHistogram.dense).
+
+    ``receiver_range`` (optional, ``(lo, hi)`` in the internal numbering) keeps only the
+    pairs whose receiver lies in that range -- the tables of one receiver shard of a
+    multi-GPU run (distributed.shard_range).  The segment / tile index spaces and
+    ``max_delay`` / ``n_directed`` stay those of the whole scene, so that every rank
+    derives the same buffer layout.
     """
     code = _lib.dtype_code(dtype)
     tdt = _lib.torch_dtype(code)
@@ -127,6 +134,12 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
         rank = rank.to(sender.device).long().contiguous()
         n_patches = int(n_internal)
         sender, receiver = rank[sender.long()], rank[receiver.long()]
+    max_delay = int(delay.max().item()) if delay.numel() else 0
+    if receiver_range is not None:
+        lo, hi = receiver_range
+        own = (receiver >= lo) & (receiver < hi)
+        sender, receiver, ff = sender[own], receiver[own], ff[own]
+        delay, out_dir, cls = delay[own], out_dir[own], cls[own]
     seg = cls.long() * n_patches + receiver.long()
     key = seg * n_patches + sender.long()
     order = torch.argsort(key)
@@ -136,7 +149,6 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
                           device=sender.device)
     seg_ptr[1:] = torch.cumsum(counts, 0)
     src = (sender[order] * n_dirs + out_dir[order].long()).to(torch.int32)
-    max_delay = int(delay.max().item()) if delay.numel() else 0
     gather = gather or gather_kind(code)
     ent_ptr = recs = win_ptr = win_recs = None
     win_w = 0

@@ -343,20 +343,29 @@ class DirectionalRadiosityFast:
     # ------------------------------------------------------------------
     # exchange: RadiosityFast.py:524-568
     # ------------------------------------------------------------------
-    def _pair_tables(self, speed_of_sound, dt, n_samples, n_shards=1):
+    def _pair_tables(self, speed_of_sound, dt, n_samples, n_shards=1, shard=None):
         """Exchange tables for (c, dt, T); ``n_shards`` > 1 numbers the patches so that
-        equal contiguous receiver shards are load-balanced (multi-GPU runs)."""
-        key = (float(speed_of_sound), float(dt), int(n_samples), self._dtype, int(n_shards))
+        equal contiguous receiver shards are load-balanced (multi-GPU runs).  ``shard``
+        (a rank index) keeps only the pairs received by that shard -- large scenes,
+        where no rank can hold the tables of the whole scene."""
+        key = (float(speed_of_sound), float(dt), int(n_samples), self._dtype, int(n_shards),
+               shard)
         if self._tables is None or self._tables[0] != key:
             b = self._baked
             delay = bake.delay_bins(b["dist"], speed_of_sound, dt).long()
             delay = torch.stack([delay, delay], dim=1).reshape(-1)
             rank, n_internal = geometry.compact_patch_order(
                 self._patches_points, self._patch_to_wall_ids, n_shards=n_shards)
+            rng = None
+            if shard is not None:
+                from .distributed import shard_range
+                lo, hi, _ = shard_range(n_internal, int(shard), int(n_shards))
+                rng = (lo, hi)
             tables = exchange.build_pair_tables(
                 b["sender"], b["receiver"], b["ff_dir"], delay, b["out_dir"], b["cls"],
                 b["coef"], self.n_patches, n_samples, self._dtype,
-                rank=torch.from_numpy(rank).to(self._device), n_internal=n_internal)
+                rank=torch.from_numpy(rank).to(self._device), n_internal=n_internal,
+                receiver_range=rng)
             self._tables = (key, tables)
         return self._tables[1]
 

@@ -36,9 +36,8 @@ def make_tables(seed=3, n=37, d=2, b=2, c=3, t_len=90):
 
 def cpu_order(sx):
     """CPU stand-in for spb_exchange_gather + spb_exchange_mix on [j_lo, j_hi)."""
-    t = sx.t
-
     def compute(prev, cur, total, b_lo, b_hi):
+        t = sx.t            # looked up per call: the band-block schedule swaps the tables
         n, nd, nc = t.n_patches, t.n_dirs, t.n_classes
         seg_ptr = t.seg_ptr.tolist()
         for j in range(sx.j_lo, sx.j_hi):
@@ -114,3 +113,114 @@ def test_sharded_exchange_world2_equals_single(tmp_path):
     h0 = sx.run(0).dense()
     for i in (0, 5, 36):
         assert torch.equal(h0[i, :, :, int(delay0[i])], e0[i])
+
+
+# ---------------------------------------------------------------------------
+# large-scene schedule: band blocks + sharded E_total + sharded receiver collection
+# ---------------------------------------------------------------------------
+def cpu_collect(hist, rdir, shift, scale):
+    """CPU stand-in for exchange.collect_mono (circular roll, RadiosityFast.py:1181-1183)."""
+    dense = hist.dense()                                   # (n, D, B, T)
+    n_rcv, n = rdir.shape
+    out = torch.zeros((n_rcv, hist.n_bands, hist.n_samples), dtype=dense.dtype)
+    for r in range(n_rcv):
+        for k in range(n):
+            for b in range(hist.n_bands):
+                sc = scale[r, k, b]
+                if sc != 0:
+                    out[r, b] += sc * torch.roll(dense[k, int(rdir[r, k]), b], int(shift[r, k]))
+    return out
+
+
+def receiver_inputs(n, d, b, t_len, seed=11):
+    gen = torch.Generator().manual_seed(seed)
+    rdir = torch.randint(0, d, (2, n), generator=gen).to(torch.int32)
+    shift = torch.randint(0, t_len, (2, n), generator=gen).to(torch.int32)
+    scale = torch.rand((2, n, b), generator=gen, dtype=torch.float64)
+    scale[:, ::3] = 0                                       # invisible patches
+    return rdir, shift, scale
+
+
+def _bandwise_worker(rank, world, port, orders, band_block, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparrowpy_b200 import distributed
+    tables, e0, delay0, t_len = make_tables(b=4)
+    bx = distributed.BandwiseExchange(tables, t_len, torch.device("cpu"),
+                                      band_block=band_block, collect=cpu_collect)
+    bx.sx.compute = cpu_order(bx.sx)
+    hist = bx.run(e0, delay0, orders)
+    mono = hist.collect_mono(*receiver_inputs(tables.n_patches, tables.n_dirs,
+                                              tables.n_bands, t_len))
+    torch.save({"local": hist.dense_local().clone(), "j": (hist.j_lo, hist.j_hi),
+                "mono": mono}, f"{out_path}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("band_block", [1, 2])
+def test_bandwise_sharded_schedule_equals_single(tmp_path, band_block):
+    from sparrowpy_b200 import distributed
+    orders = 2
+    tables, e0, delay0, t_len = make_tables(b=4)
+    sx = distributed.ShardedExchange(tables, t_len, torch.device("cpu"))
+    sx.compute = cpu_order(sx)
+    sx.init(e0, delay0)
+    full_hist = sx.run(orders)
+    full = full_hist.dense().clone()
+    rcv = receiver_inputs(tables.n_patches, tables.n_dirs, tables.n_bands, t_len)
+    mono_ref = cpu_collect(full_hist, *rcv)
+    # one process: band blocks only
+    bx = distributed.BandwiseExchange(tables, t_len, torch.device("cpu"),
+                                      band_block=band_block, collect=cpu_collect)
+    bx.sx.compute = cpu_order(bx.sx)
+    h1 = bx.run(e0, delay0, orders)
+    assert torch.equal(h1.dense_local(), full)
+    assert torch.allclose(h1.collect_mono(*rcv), mono_ref, rtol=1e-13, atol=0)
+    # two ranks: every rank keeps its own receivers only; the collection is all-reduced
+    out = str(tmp_path / "bw")
+    mp.spawn(_bandwise_worker, args=(2, _free_port(), orders, band_block, out), nprocs=2,
+             join=True)
+    parts = [torch.load(f"{out}.{r}") for r in range(2)]
+    got = torch.cat([p["local"] for p in parts])
+    assert [p["j"] for p in parts] == [(0, 24), (24, 37)]
+    assert torch.equal(got, full)
+    for p in parts:
+        assert torch.allclose(p["mono"], mono_ref, rtol=1e-13, atol=0)
+
+
+def test_shard_restricted_tables_partition_the_full_tables():
+    """build_pair_tables(receiver_range=...) keeps exactly the rank's segments; layout
+    quantities stay global."""
+    from sparrowpy_b200 import exchange
+    from sparrowpy_b200.distributed import shard_range
+    from test_tables_cpu import random_pairs
+    sender, receiver, ff, delay, out_dir, cls, coef, n, t_len = random_pairs(7)
+    full = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n, t_len,
+                                      "f64")
+    world = 3
+    seen = 0
+    for r in range(world):
+        lo, hi, _ = shard_range(n, r, world)
+        part = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n,
+                                          t_len, "f64", receiver_range=(lo, hi))
+        assert (part.max_delay, part.n_directed) == (full.max_delay, full.n_directed)
+        cnt_full = (full.seg_ptr[1:] - full.seg_ptr[:-1]).view(full.n_classes, n)
+        cnt_part = (part.seg_ptr[1:] - part.seg_ptr[:-1]).view(full.n_classes, n)
+        assert torch.equal(cnt_part[:, lo:hi], cnt_full[:, lo:hi])
+        assert int(cnt_part.sum()) == int(cnt_full[:, lo:hi].sum())
+        for c in range(full.n_classes):
+            for j in range(lo, hi):
+                a0, a1 = full.seg_ptr[c * n + j], full.seg_ptr[c * n + j + 1]
+                b0, b1 = part.seg_ptr[c * n + j], part.seg_ptr[c * n + j + 1]
+                assert torch.equal(full.src[a0:a1], part.src[b0:b1])
+                assert torch.equal(full.dly[a0:a1], part.dly[b0:b1])
+                assert torch.equal(full.wgt[a0:a1], part.wgt[b0:b1])
+        # tile records of the shard's tiles are those of the full tables
+        rec_full = (full.ent_ptr[1:] - full.ent_ptr[:-1]).view(full.n_classes, -1)
+        rec_part = (part.ent_ptr[1:] - part.ent_ptr[:-1]).view(full.n_classes, -1)
+        assert torch.equal(rec_part[:, lo // 8:-(-hi // 8)], rec_full[:, lo // 8:-(-hi // 8)])
+        seen += int(cnt_part.sum())
+    assert seen == full.src.numel()

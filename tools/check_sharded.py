@@ -59,7 +59,6 @@ for dtype in ("f64", "f32"):
         bx = distributed.BandwiseExchange(part, n_samples, dev, band_block=block)
         h = bx.run(rad._e0_dev, delay0, orders)
         torch.cuda.synchronize()
-        mine = ref.index_select(0, torch.argsort(tables.rank))       # internal order
         inv = torch.full((tables.n_patches,), -1, dtype=torch.long, device=dev)
         inv[tables.rank] = torch.arange(tables.n_user, device=dev)
         own = inv[h.j_lo:h.j_hi]
@@ -69,7 +68,7 @@ for dtype in ("f64", "f32"):
         ok &= same
         if rank == 0:
             print(f"{dtype} bandwise block={block}: own rows equal={same}", flush=True)
-        del bx, h, mine
+        del bx, h
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -261,8 +261,12 @@ k_gather_win(const double *__restrict__ e_prev, double *__restrict__ g,
 //     once per record and warp.  full[s] counts the 32 lanes of the copying warp.
 //   * the per-(record, receiver) dispatch is one indirect branch through a jump table
 //     (win_dispatch.cuh, `brx.idx`) instead of a compare tree.
+// Variant 3 (window + 300, SPB_WIN_VARIANT=3) = variant 2 with the whole record in one
+// chained dispatch (CHAIN = true): the dispatch of receiver s + 1 is duplicated into
+// every case of receiver s, so there is no branch back to a join point and the next
+// table lookup overlaps the DFMAs of the current case.
 // ---------------------------------------------------------------------------------
-template <int W>
+template <int W, bool CHAIN>
 __global__ void __launch_bounds__(kCtaT / 8, 1)
 k_gather_win2(const double *__restrict__ e_prev, double *__restrict__ g,
               const int64_t *__restrict__ ent_ptr, const WinRecord *__restrict__ recs,
@@ -354,9 +358,21 @@ k_gather_win2(const double *__restrict__ e_prev, double *__restrict__ g,
         }
         const WinRecord *rec = reinterpret_cast<const WinRecord *>(sw + win_stride);
         const uint64_t rel = *reinterpret_cast<const uint64_t *>(rec->rel);
+        if constexpr (CHAIN) {
+            double w[kR];
 #pragma unroll
-        for (int s = 0; s < kR; ++s)
-            accumulate_brx<W, LT>(acc[s], rec->w[s], win, (unsigned)((rel >> (8 * s)) & 0xffu));
+            for (int s = 0; s < kR; s += 2) {
+                const double2 x = *reinterpret_cast<const double2 *>(&rec->w[s]);
+                w[s] = x.x;
+                w[s + 1] = x.y;
+            }
+            accumulate_chain<W>(acc, w, win, (unsigned)rel, (unsigned)(rel >> 32));
+        } else {
+#pragma unroll
+            for (int s = 0; s < kR; ++s)
+                accumulate_brx<W, LT>(acc[s], rec->w[s], win,
+                                      (unsigned)((rel >> (8 * s)) & 0xffu));
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -402,11 +418,12 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
     const int win_stride = (win_bytes + 511) / 512 * 512;
     const size_t smem = (size_t)(win_stride + kRecPad) * kStages + 2 * kStages * sizeof(uint64_t);
     dim3 grid((unsigned)n_cta, (unsigned)n_y);
-    if constexpr (VARIANT == 2) {
-        static_assert(LT == 8, "variant 2 has 8 bins per lane");
-        SPB_CUDA(cudaFuncSetAttribute(k_gather_win2<W>,
+    if constexpr (VARIANT >= 2) {
+        static_assert(LT == 8, "variants 2 and 3 have 8 bins per lane");
+        constexpr bool kChain = VARIANT == 3;
+        SPB_CUDA(cudaFuncSetAttribute(k_gather_win2<W, kChain>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gather_win2<W><<<grid, n_warps * 32, smem, st>>>(
+        k_gather_win2<W, kChain><<<grid, n_warps * 32, smem, st>>>(
             e_prev, g, ent_ptr, recs, n_patches, n_alloc, n_blocks, n_dirs, b_lo, jb_lo, n_jb,
             n_classes, t_pad, ld, pad, n_warps, win_stride, cta_order);
         return check_launch("k_gather_win2");
@@ -460,12 +477,15 @@ int spb_exchange_gather_window(const void *e_prev, void *g, const int64_t *ent_p
                                     t_pad, ld, pad, st)
     // window + 100: tuning variant with 4 bins per lane and up to 16 warps per CTA
     // window + 200: variant 2 (row copied by one warp per record, jump-table dispatch)
+    // window + 300: variant 3 (variant 2 with one chained dispatch per record)
     if (window == 4) SPB_WIN_LAUNCH(4, 8, 1);
     if (window == 10) SPB_WIN_LAUNCH(10, 8, 1);
     if (window == 104) SPB_WIN_LAUNCH(4, 4, 1);
     if (window == 110) SPB_WIN_LAUNCH(10, 4, 1);
     if (window == 204) SPB_WIN_LAUNCH(4, 8, 2);
     if (window == 210) SPB_WIN_LAUNCH(10, 8, 2);
+    if (window == 304) SPB_WIN_LAUNCH(4, 8, 3);
+    if (window == 310) SPB_WIN_LAUNCH(10, 8, 3);
 #undef SPB_WIN_LAUNCH
     return fail(-1, "invalid argument", "window must be 4 or 10");
 }

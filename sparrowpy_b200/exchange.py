@@ -96,10 +96,12 @@ def gather_kind(code=None):
 def window_arg(tables):
     """``window`` argument of spb_exchange_gather_window: the record window, plus a
     tuning variant selected by the environment -- +100: 4 instead of 8 time bins per
-    lane (``SPB_WIN_LANE_T=4``); +200: variant 2, row copied by one warp per record and
-    jump-table dispatch (``SPB_WIN_VARIANT=2``; compiled but not yet run on a GPU)."""
-    if os.environ.get("SPB_WIN_VARIANT", "1") == "2":
-        return tables.win_w + 200
+    lane (``SPB_WIN_LANE_T=4``); +200 / +300: variants 2 and 3, row copied by one warp per
+    record and jump-table dispatch per receiver / chained per record
+    (``SPB_WIN_VARIANT=2|3``; compiled but not yet run on a GPU)."""
+    variant = os.environ.get("SPB_WIN_VARIANT", "1")
+    if variant in ("2", "3"):
+        return tables.win_w + 100 * int(variant)
     return tables.win_w + (100 if os.environ.get("SPB_WIN_LANE_T", "8") == "4" else 0)
 
 

@@ -41,7 +41,8 @@ def ragged(seed, n, d, c, m, max_delay, spread, dev):
 @pytest.mark.parametrize("t_len,spread,width", [
     (300, 3, 4), (300, 9, 10), (300, 25, 10), (1000, 9, 4), (1200, 6, 10), (2000, 9, 10),
     (2300, 10, 10), (5000, 4, 4)])
-@pytest.mark.parametrize("lane_t", [8, 4, pytest.param("v2", marks=EXPERIMENTAL)])
+@pytest.mark.parametrize("lane_t", [8, 4, pytest.param("v2", marks=EXPERIMENTAL),
+                                    pytest.param("v3", marks=EXPERIMENTAL)])
 def test_window_gather_equals_csr_gather(t_len, spread, width, lane_t, monkeypatch):
     from sparrowpy_b200 import _lib, exchange
     monkeypatch.setenv("SPB_GATHER", "win")
@@ -66,12 +67,12 @@ def test_window_gather_equals_csr_gather(t_len, spread, width, lane_t, monkeypat
     g1 = torch.zeros((b * c * n, ld), dtype=torch.float64, device=dev)
     g2 = torch.zeros_like(g1)
     st, code = _lib.stream_ptr(), _lib.I32(tables.dtype)
-    if lane_t == "v2":
-        monkeypatch.setenv("SPB_WIN_VARIANT", "2")
+    if lane_t in ("v2", "v3"):
+        monkeypatch.setenv("SPB_WIN_VARIANT", lane_t[1])
     else:
         monkeypatch.setenv("SPB_WIN_LANE_T", str(lane_t))
     win_arg = exchange.window_arg(tables)
-    assert win_arg == width + {8: 0, 4: 100, "v2": 200}[lane_t]
+    assert win_arg == width + {8: 0, 4: 100, "v2": 200, "v3": 300}[lane_t]
     _lib.call("spb_exchange_gather", prev, g1, tables.seg_ptr, tables.src, tables.wgt,
               tables.dly, n, n, c, d, b, 0, b, 0, n, t_pad, ld, pad, code, st)
     _lib.call("spb_exchange_gather_window", prev, g2, tables.win_ptr, tables.win_recs, None, n,

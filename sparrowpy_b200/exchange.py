@@ -257,9 +257,12 @@ def window_geometry(code):
 WINDOW_CHOICES = (4, 10)     # instantiations of k_gather_win
 
 
-def _window_cover(delay_sorted, group, pos, n_groups, n_r, width):
-    """Greedy cover of every group's sorted delays by windows [base, base + width],
-    base even.  Returns (starts_new_record (bool), base per entry)."""
+def _window_cover(delay_sorted, group, pos, n_groups, n_r, width, align=2):
+    """Greedy cover of every group's sorted delays by windows [base, base + width] with
+    ``(base + width) % align == 0`` (``align`` = 2: even base, the staged row starts on
+    a 16-byte boundary; 4: on a 32-byte sector boundary, at the price of a window that
+    starts up to 3 bins before the first delay).  Returns (starts_new_record (bool),
+    base per entry)."""
     dev = delay_sorted.device
     base = torch.zeros(n_groups, dtype=torch.int64, device=dev)
     start = torch.zeros(delay_sorted.numel(), dtype=torch.bool, device=dev)
@@ -270,14 +273,15 @@ def _window_cover(delay_sorted, group, pos, n_groups, n_r, width):
             break
         gp, dp = group[idx], delay_sorted[idx]
         new = dp > base[gp] + width if p else torch.ones_like(dp, dtype=torch.bool)
-        base[gp[new]] = dp[new] & ~1
+        nb = dp[new] - (dp[new] + width) % align
+        base[gp[new]] = torch.where(nb < 0, dp[new] & ~1, nb)
         start[idx] = new
         ebase[idx] = base[gp]
     return start, ebase
 
 
 def build_window_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs,
-                         n_classes, code, width=None):
+                         n_classes, code, width=None, align=None):
     """Records of the register-window gather (csrc/exchange_win.cu).
 
     A tile is R neighbouring receivers of one class.  The directed pairs of one
@@ -285,9 +289,15 @@ def build_window_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n
     ``[dbase, dbase + W]`` with ``dbase`` even; each window is one record
     ``{w[R] f64, rel[R] u8 (delay - dbase, 255 = no pair), src i32, dbase i32}``.
     ``W`` is the narrowest instantiated window that costs at most 2 % more records than
-    the widest one.  Pure index bookkeeping (sort / cumsum / scatter).
-    Returns ``(ent_ptr, recs, W)``.
+    the widest one.  ``align`` (default 2, or ``SPB_WIN_ALIGN``) = 4 makes the staged rows
+    start on 32-byte sector boundaries (profiles/r01_k_gather_win_c4_f64.txt: rows that
+    start in mid-sector cost twice the L2 traffic).  Pure index bookkeeping (sort /
+    cumsum / scatter).  Returns ``(ent_ptr, recs, W)``.
     """
+    if align is None:
+        align = int(os.environ.get("SPB_WIN_ALIGN", "2"))
+    if align not in (2, 4):
+        raise ValueError("window alignment must be 2 or 4 bins")
     n_r, max_w, rec_bytes = window_geometry(code)
     tdt = _lib.torch_dtype(code)
     dev = sender.device
@@ -311,7 +321,7 @@ def build_window_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n
     pos = torch.arange(gk.numel(), device=dev) - g_start[group]
     assert int(pos.max().item()) < n_r, "more pairs than receiver slots in a group"
     widths = [w for w in WINDOW_CHOICES if w <= max_w] if width is None else [int(width)]
-    covers = {w: _window_cover(d, group, pos, n_groups, n_r, w) for w in widths}
+    covers = {w: _window_cover(d, group, pos, n_groups, n_r, w, align) for w in widths}
     n_wide = int(covers[widths[-1]][0].sum().item())
     width = next(w for w in widths if int(covers[w][0].sum().item()) <= 1.02 * n_wide)
     start, ebase = covers[width]

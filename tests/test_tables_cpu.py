@@ -147,13 +147,20 @@ def decode_window_records(ent_ptr, recs, width, n_patches, n_r=8):
     return sorted(out)
 
 
+@pytest.mark.parametrize("align", [2, 4])
 @pytest.mark.parametrize("width", [None, 4, 10])
-def test_window_records_encode_the_same_pairs(width):
+def test_window_records_encode_the_same_pairs(width, align):
     sender, receiver, ff, delay, out_dir, cls, coef, n, t_len = random_pairs(3)
     keep = delay < t_len
     args = [x[keep] for x in (sender, receiver, ff, delay, out_dir, cls)]
-    ent_ptr, recs, w = exchange.build_window_records(*args, n, 3, 4, _lib.F64, width=width)
+    ent_ptr, recs, w = exchange.build_window_records(*args, n, 3, 4, _lib.F64, width=width,
+                                                     align=align)
     assert w in exchange.WINDOW_CHOICES and (width is None or w == width)
+    dbase = recs.numpy()[:, 76:80].copy().view(np.int32).reshape(-1)
+    first = np.array([r[64:72][r[64:72] != 255].min() for r in recs.numpy()])
+    # sector-aligned rows wherever a non-negative base with that residue exists
+    ok = (dbase + w) % align == 0
+    assert ok[dbase + first >= align].all() and (dbase % 2 == 0).all()
     want = sorted((int(c), int(r), int(s) * 3 + int(o), int(dl), float(x))
                   for s, r, x, dl, o, c in zip(*args))
     assert decode_window_records(ent_ptr, recs, w, n) == want

@@ -57,9 +57,21 @@ def visibility_pt2p(points, centers, surf_normals, surf_points, blockers=None):
     return vis.bool()
 
 
-def visible_pairs(vis):
-    """Row-major (P, 2) int32 list of visible pairs (RadiosityFast.py:377-387)."""
-    return torch.nonzero(vis).to(torch.int32).contiguous()
+def visible_pairs(vis, max_block_elems=1 << 30):
+    """Row-major (P, 2) int32 list of visible pairs (RadiosityFast.py:377-387).
+
+    The matrix is scanned in blocks of rows: ``torch.nonzero`` handles at most 2^31
+    elements per call, and config 5 (N = 100 000) has 10^10."""
+    n_rows, n_cols = vis.shape
+    step = max(1, int(max_block_elems // max(1, n_cols)))
+    if step >= n_rows:
+        return torch.nonzero(vis).to(torch.int32).contiguous()
+    parts = []
+    for r0 in range(0, n_rows, step):
+        idx = torch.nonzero(vis[r0:r0 + step]).to(torch.int32)
+        idx[:, 0] += r0
+        parts.append(idx)
+    return torch.cat(parts).contiguous()
 
 
 def form_factors(points, normals, areas, pairs):

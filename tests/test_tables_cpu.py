@@ -207,3 +207,16 @@ def test_window_swizzle_is_conflict_free():
                 groups = {swz4(64 * warp + 2 * lane + q) % 8
                           for lane in range(8 * quarter, 8 * quarter + 8)}
                 assert len(groups) == 8
+
+
+def test_visible_pairs_scans_the_matrix_in_row_blocks():
+    """bake.visible_pairs must not depend on the block size (torch.nonzero is limited to
+    2^31 elements per call; config 5 has a 10^10-element visibility matrix)."""
+    from sparrowpy_b200 import bake
+    gen = torch.Generator().manual_seed(0)
+    vis = torch.triu(torch.rand((57, 57), generator=gen) < 0.2, 1)
+    whole = bake.visible_pairs(vis)
+    assert whole.dtype == torch.int32 and whole.shape[1] == 2
+    assert torch.equal(whole.long(), torch.nonzero(vis))
+    for block in (1, 57, 100, 57 * 5 + 3, 57 * 57):
+        assert torch.equal(bake.visible_pairs(vis, max_block_elems=block), whole)

@@ -280,12 +280,15 @@ class DirectionalRadiosityFast:
             raise ValueError(
                 "source must be pf.Coordinates or sparrowpy SoundSource")
         self._source = source
-        if getattr(source, "directivity", None) is not None:
-            raise NotImplementedError(
-                "source directivities (DirectivityMS / SOFA) are outside the B200 "
-                "hot path; see DESIGN.md")
         svis, d0, e0 = self._source_energy(source_position[None])
         self._source_vis_dev, self._d0_dev, self._e0_dev = svis[0], d0[0], e0[0]
+        if getattr(source, "directivity", None) is not None:
+            # one real factor per (patch, band), the same for every outgoing direction
+            # (RadiosityFast.py:497-517); evaluated on the host, applied on the device
+            fac = np.stack([np.real(source.get_directivity(self.patches_center, f))
+                            for f in self._frequencies], axis=-1)
+            self._e0_dev = self._e0_dev * torch.from_numpy(
+                np.ascontiguousarray(fac, dtype=float)).to(self._device)[:, None, :]
         self._host["energy_init_source"] = None
         self._host["distance_patches_to_source"] = None
 
@@ -493,7 +496,10 @@ class DirectionalRadiosityFast:
             for i in range(self.n_bins):
                 direct_sound[:, i] *= np.exp(-np.real(self._air_attenuation[i]) * r)
         if getattr(self._source, "directivity", None) is not None:
-            raise NotImplementedError("source directivity is outside the B200 hot path")
+            rcv = np.asarray(receivers.cartesian, float).reshape(-1, 3)
+            for i in range(self.n_bins):
+                direct_sound[:, i] *= np.real(np.atleast_1d(self._source.get_directivity(
+                    np.squeeze(rcv), self._frequencies[i])))
         n_sample_delay = np.array(
             r / self.speed_of_sound / self._etc_time_resolution, dtype=int)
         return direct_sound, n_sample_delay

@@ -390,6 +390,30 @@ def gen_point_patch():
     save("point_patch", patches=P, points=Q, source=src, receiver=rcv)
 
 
+def gen_directivity_metrics():
+    """Azimuth / elevation of a target in the source frame: the reference's
+    sound_object._get_metrics (sound_object.py:67-87), pure numpy."""
+    from sparrowpy import sound_object as so
+    rng = np.random.default_rng(42)
+    n = 300
+    pos, tgt = rng.uniform(-3, 3, (n, 3)), rng.uniform(-6, 6, (n, 3))
+    view = rng.normal(size=(n, 3))
+    view /= np.linalg.norm(view, axis=1)[:, None]
+    up = rng.normal(size=(n, 3))
+    up -= np.sum(up * view, 1)[:, None] * view
+    up /= np.linalg.norm(up, axis=1)[:, None]
+    # axis-aligned frames with targets on the axes (branch cuts of arctan2 / arcsin)
+    view[:6] = [[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [1, 0, 0]]
+    up[:6] = [[0, 0, 1], [0, 0, 1], [1, 0, 0], [0, 0, 1], [0, 0, 1], [0, 1, 0]]
+    tgt[:6] = pos[:6] + np.array([[1, 0, 0], [0, 0, 2], [0, 1, 0], [1, 1, 0], [0, 0, -1],
+                                  [0, -3, 0]])
+    az, el = np.zeros(n), np.zeros(n)
+    for k in range(n):
+        az[k], el[k] = so._get_metrics(pos[k], view[k], up[k], tgt[k])
+    save("directivity_metrics", pos=pos, view=view, up=up, target=tgt, azimuth_deg=az,
+         elevation_deg=el)
+
+
 def main():
     only = set(sys.argv[1:])
 
@@ -406,6 +430,8 @@ def main():
         print("form factor pairs"); gen_form_factor_pairs()
     if want("ptpatch"):
         print("point-patch"); gen_point_patch()
+    if want("directivity"):
+        print("directivity metrics"); gen_directivity_metrics()
 
     if want("cube"):
         print("scene cube05 (reference tests/test_DRadiosityFast.py:19-29)")

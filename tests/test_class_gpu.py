@@ -255,3 +255,51 @@ def test_ground_plane_multi_source_multi_receiver(oracle):
                               np.full((1, 1, 1, 1), np.pi), np.zeros(1, np.int64))
         assert rel_err(mono[s], ref["etc_receiver_mono"]) < 1e-6
         assert rel_err(rad._energy_exchange_etc[s], ref["etc"]) < 1e-6
+
+
+def test_source_directivity_scales_initial_energy_and_direct_sound():
+    """A SoundSource with a directivity: one real factor per (patch, band) on the initial
+    energy, the same for every outgoing direction (RadiosityFast.py:497-517), and one
+    per (receiver, band) on the direct sound (:648-651)."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf, scenes, sound_object as so
+    dirs4, w4 = scenes.hemisphere_directions(4, (45.0,))
+    freqs = np.array([500.0, 2000.0])
+    brdf = scenes.brdf_from_scattering(dirs4, w4, [0.5, 0.7], [0.1, 0.2])
+    coords = pf.Coordinates.from_cartesian(dirs4, weights=w4)
+
+    def make(source):
+        rad = sp.DirectionalRadiosityFast.from_polygon(sp.testing.shoebox_room_stub(3, 2, 2),
+                                                       0.5)
+        rad.set_wall_brdf(np.arange(6), pf.FrequencyData(brdf, freqs), coords, coords)
+        rad.set_air_attenuation(pf.FrequencyData([1e-3, 4e-3], freqs))
+        rad.bake_geometry()
+        rad.init_source_energy(source)
+        return rad
+
+    rng = np.random.default_rng(3)
+    sphere = rng.normal(size=(60, 3))
+    sphere /= np.linalg.norm(sphere, axis=1)[:, None]
+    data = rng.uniform(0.2, 1.5, (60, 3))
+    directivity = so.DirectivityMS.from_arrays(data, [400.0, 1000.0, 2500.0], sphere)
+    pos = [1.1, 0.9, 1.2]
+    omni = make(pf.Coordinates(*pos))
+    src = so.SoundSource(pos, [1, 0, 0], [0, 0, 1], directivity=directivity)
+    rad = make(src)
+    e_omni, e_dir = omni._energy_init_source, rad._energy_init_source
+    assert e_dir.shape == e_omni.shape == (rad.n_patches, 4, 2)
+    fac = np.stack([src.get_directivity(rad.patches_center, f) for f in freqs], -1)
+    assert fac.shape == (rad.n_patches, 2) and fac.min() > 0
+    np.testing.assert_allclose(e_dir, e_omni * fac[:, None, :], rtol=1e-14)
+    assert np.array_equal(rad._distance_patches_to_source, omni._distance_patches_to_source)
+    # the exchange is linear in the initial energy: directivity scales what it feeds
+    for r_ in (omni, rad):
+        r_.calculate_energy_exchange(343.2, 0.5e-3, 0.02, max_reflection_order=2)
+    rcv = pf.Coordinates.from_cartesian(np.array([[2.2, 1.3, 0.7], [0.4, 0.5, 1.6]]))
+    d_omni, k_omni = omni.calculate_direct_sound(rcv)
+    d_dir, k_dir = rad.calculate_direct_sound(rcv)
+    fac_r = np.stack([src.get_directivity(rcv.cartesian, f) for f in freqs], -1)
+    np.testing.assert_allclose(d_dir, d_omni * fac_r, rtol=1e-14)
+    assert np.array_equal(k_dir, k_omni)
+    etc = rad.collect_energy_receiver_mono(rcv, direct_sound=True).time
+    assert etc.shape == (2, 2, 40) and np.isfinite(etc).all() and etc.sum() > 0

@@ -50,8 +50,9 @@ def decode_records(t, dtype=np.float64):
                     assert bool(mask >> s & 1) == (cur != rel[s])
                     cur = rel[s]
                 else:
+                    # empty slots never trigger a reload and repeat the current shift
                     assert not (mask >> s & 1)
-                    assert cur is None or rel[s] == cur or True
+                    assert rel[s] == (0 if cur is None else cur)
     return sorted(out)
 
 

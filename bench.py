@@ -408,6 +408,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic,
+                "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0,
                 "kernel": ("k_gather_win" if tables.win_recs is not None and
                            args.gather == "win" else
                            "k_gather" if args.gather == "csr" else "k_gather_tma"),

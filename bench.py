@@ -520,6 +520,11 @@ def run_large(args, cfg, rank, world, local_rank, warmup, log):
     n_samples, orders = cfg["n_samples"], cfg["orders"]
     tables = rad._pair_tables(SPEED_OF_SOUND, DT, n_samples, n_shards=world,
                               shard=rank if world > 1 else None)
+    # the per-pair bake tensors of the whole scene (visibility matrix, form factors,
+    # direction indices: ~60 GB for config 5) are not needed once this rank's tables exist
+    rad._baked = None
+    rad._tables = None
+    torch.cuda.empty_cache()
     code = _lib.dtype_code(args.dtype)
     esize = 8 if code == _lib.F64 else 4
     n_dir, n_band = tables.n_dirs, tables.n_bands

@@ -467,6 +467,30 @@ def main():
                   directions=(d4, w4), air=np.array([1e-3, 4e-3]),
                   frequencies=freqs, etc_rows=np.arange(0, 128, 8),
                   store_tilde_rows=[0, 5, 50, 101, 127])
+    if want("uneven"):
+        # patch size that does not divide the walls: int(size / patch) truncation
+        # (geometry.py:330-345) gives 0.75 x 0.7 x 0.7 m patches; two BRDF sets, air
+        print("scene uneven (non-dividing patch size, two BRDF sets)")
+        d4, w4 = scenes.hemisphere_directions(4, (45.0,))
+        b0 = scenes.brdf_from_scattering(d4, w4, [0.3, 0.9], [0.15, 0.1])
+        b1 = scenes.brdf_from_scattering(d4, w4, [0.8, 0.2], [0.05, 0.3])
+        run_scene("scene_uneven", scenes.shoebox(3, 2.1, 1.4), 0.7,
+                  source=[0.9, 1.3, 0.6], receivers=[[2.4, 0.5, 1.0], [0.3, 1.8, 0.2]],
+                  c=343.2, dt=0.25e-3, duration=0.025, max_order=3,
+                  brdf_sets=[([0, 2, 4], b0), ([1, 3, 5], b1)],
+                  directions=(d4, w4), air=np.array([2e-3, 9e-3]),
+                  frequencies=[250.0, 4000.0])
+    if want("canyondir"):
+        print("scene canyon (scale 0.15) with a directional BRDF")
+        d4, w4 = scenes.hemisphere_directions(4, (45.0,))
+        b0 = scenes.brdf_from_scattering(d4, w4, [0.4, 0.8], [0.2, 0.1])
+        walls = scenes.street_canyon(seed=1, scale=0.15)
+        run_scene("scene_canyon015_dir", walls, 1.0,
+                  source=[2.5, 4.5, 1.5], receivers=[[15.5, 4.5, 1.5], [9.5, 3.5, 2.5]],
+                  c=343.2, dt=0.5e-3, duration=0.1, max_order=3,
+                  brdf_sets=[(np.arange(len(walls)), b0)], directions=(d4, w4),
+                  air=np.array([1e-3, 5e-3]), frequencies=[500.0, 2000.0],
+                  etc_rows=np.arange(0, 400, 25), store_tilde_rows=[0, 100, 399])
     if want("canyon"):
         print("scene canyon (scale 0.1)")
         run_scene("scene_canyon01", scenes.street_canyon(seed=0, scale=0.1), 1.0,

@@ -4,12 +4,11 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import GPU_SCENES, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-SCENES = ["scene_cube05", "scene_c1", "scene_occluder", "scene_directional",
-          "scene_canyon01"]
+SCENES = GPU_SCENES
 
 
 def T(a, dtype=None):

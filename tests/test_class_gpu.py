@@ -3,11 +3,10 @@ was when the golden fixtures were made (tests/golden/make_golden.py::run_scene).
 import numpy as np
 import pytest
 
-from conftest import load_golden, rel_err
+from conftest import GPU_SCENES, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
-SCENES = ["scene_cube05", "scene_c1", "scene_occluder", "scene_directional",
-          "scene_canyon01"]
+SCENES = GPU_SCENES
 TOL = {"f64": 1e-6, "f32": 1e-4}
 
 

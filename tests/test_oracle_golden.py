@@ -6,7 +6,7 @@ import pytest
 from conftest import load_golden, rel_err
 
 SCENES = ["scene_cube05", "scene_c1", "scene_occluder", "scene_directional",
-          "scene_canyon01"]
+          "scene_canyon01", "scene_uneven", "scene_canyon015_dir"]
 
 
 def test_rounding_model(oracle):

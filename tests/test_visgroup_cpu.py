@@ -16,7 +16,8 @@ def grouped(oracle, cen, nrm, pts, ids):
 
 
 @pytest.mark.parametrize("name", ["scene_cube05", "scene_c1", "scene_occluder",
-                                  "scene_directional", "scene_canyon01"])
+                                  "scene_directional", "scene_canyon01", "scene_uneven",
+                                  "scene_canyon015_dir"])
 def test_golden_scenes(oracle, name):
     g = load_golden(name)
     n = len(g["patches_center"])

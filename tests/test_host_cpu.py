@@ -37,8 +37,26 @@ def test_scene_sizes():
     assert n_patches(scenes.shoebox(5, 6, 4), 0.2) == 3700           # config 2
     assert n_patches(scenes.street_canyon(), 1.0) == 19200           # config 4
     assert n_patches(scenes.ground_plane(-50, 50, -50, 50), 0.5) == 40000   # config 3
-    for w in scenes.street_canyon() + scenes.city_block():
-        geometry.Polygon(*w)                                         # planarity / normal asserts
+    assert n_patches(scenes.city_block(), 0.5) == 100000             # config 5
+    # bench.py's configurations build these scenes; sources / receivers stand in the street
+    import bench
+    for name, n in (("c1", 148), ("c2", 3700), ("c4", 19200), ("c5", 100000), ("c5s", 6280)):
+        cfg = bench.CONFIGS[name]
+        kind, arg = cfg["scene"]
+        walls = (scenes.shoebox(*arg) if kind == "shoebox" else
+                 scenes.city_block(0, arg) if kind == "city" else scenes.street_canyon(0, arg))
+        assert n_patches(walls, cfg["patch"]) == n, name
+        pts = np.array([w[0] for w in walls])
+        lo, hi = pts.reshape(-1, 3).min(0), pts.reshape(-1, 3).max(0)
+        for p in [cfg["source"]] + list(cfg["receivers"]):
+            assert np.all(np.asarray(p) >= lo - 1e-9) and np.all(np.asarray(p) <= hi + 1e-9)
+            if kind != "shoebox":                 # not inside a building (4 facades each)
+                assert (len(walls) - 1) % 4 == 0
+                for k in range(1, len(walls), 4):
+                    q = np.concatenate([np.asarray(w[0]) for w in walls[k:k + 4]])
+                    inside = (q[:, 0].min() < p[0] < q[:, 0].max() and
+                              q[:, 1].min() < p[1] < q[:, 1].max())
+                    assert not inside, (name, p)
 
 
 def test_visibility_predicate_shortcuts_match_oracle(tmp_path):

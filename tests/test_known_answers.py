@@ -236,3 +236,74 @@ def test_point_visibility_behind_a_plate(impl):
             if min(abs(hit[1] - 1), abs(hit[1] - 3), abs(hit[2] - 1), abs(hit[2] - 3)) < 1e-3:
                 continue
             assert vis[k] == (not (1 < hit[1] < 3 and 1 < hit[2] < 3)), k
+
+
+# ---------------------------------------------------------------------------
+# infinite diffuse plane (Svensson & Savioja 2024), reference
+# tests/test_DRadiosityFast_infinite_diffuse_plane.py: order 0 on one 20 x 20 m ground
+# polygon, 1 m patches, 1 s ETC in ONE bin; ratio of diffuse to specular energy
+# ---------------------------------------------------------------------------
+def plane_ratio_oracle(oracle, source, receiver):
+    half = 10.0
+    wall = rect([-half, -half, 0], [2 * half, 0, 0], [0, 2 * half, 0])[None]
+    one = np.array([[[0.0, 0.0, 1.0]]])
+    out = oracle.pipeline(wall, np.array([[0.0, 0.0, 1.0]]), 1.0, np.asarray(source, float),
+                          np.asarray(receiver, float)[None], 343.0, 1.0, 1.0, 0, np.zeros(1),
+                          one, one, np.ones((1, 1, 1, 1)), np.zeros(1, np.int64),
+                          brdf_set_before_bake=True)
+    return float(out["etc_receiver_mono"].sum())
+
+
+def plane_ratio_cuda(source, receiver):
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    half = 10.0
+    plane = sp.Polygon(rect([-half, -half, 0], [2 * half, 0, 0], [0, 2 * half, 0]),
+                       [1, 0, 0], [0, 0, 1])
+    rad = sp.DirectionalRadiosityFast.from_polygon([plane], 1.0)
+    dirs = pf.Coordinates(0, 0, 1, weights=1)
+    brdf = sp.brdf.create_from_scattering(dirs, dirs, pf.FrequencyData(1, [100]),
+                                          pf.FrequencyData(0, [100]))
+    rad.set_wall_brdf(np.arange(1), brdf, dirs, dirs)
+    rad.set_air_attenuation(pf.FrequencyData(np.zeros(1), [100]))
+    rad.init_source_energy(pf.Coordinates(*source))
+    rad.calculate_energy_exchange(speed_of_sound=343, etc_time_resolution=1.0,
+                                  etc_duration=1, max_reflection_order=0)
+    etc = rad.collect_energy_receiver_mono(pf.Coordinates(*receiver))
+    return float(np.sum(etc.time))
+
+
+UNVERIFIED_GPU = pytest.mark.skipif(
+    __import__("os").environ.get("SPB_EXPERIMENTAL") != "1",
+    reason="one-bin histograms have not run on a GPU yet (set SPB_EXPERIMENTAL=1)")
+
+
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=[pytest.mark.gpu, UNVERIFIED_GPU])])
+def plane_ratio(request, oracle):
+    def ratio(source, receiver):
+        image = np.array([source[0], source[1], -source[2]])
+        specular = 1 / (4 * np.pi * np.sum((np.asarray(receiver) - image) ** 2))
+        diffuse = (plane_ratio_oracle(oracle, source, receiver) if request.param == "oracle"
+                   else plane_ratio_cuda(source, receiver))
+        return diffuse / specular
+    return ratio
+
+
+@pytest.mark.parametrize("source, receiver", [((0, 0, 3), (0, 0, 3)), ((0, 0, 5), (0, 0, 3))])
+def test_diffuse_plane_along_the_normal(plane_ratio, source, receiver):
+    """cases 1 and 2 of the paper: ratio 2 for an infinite plane, 1.97 for 20 x 20 m
+    (reference tests/test_DRadiosityFast_infinite_diffuse_plane.py:93-131)"""
+    ratio = plane_ratio(source, receiver)
+    assert ratio < 2
+    assert abs(ratio - 1.97) / 1.97 < 0.01
+
+
+@pytest.mark.parametrize("theta_deg", [30, 45, 60])
+def test_diffuse_plane_same_height(plane_ratio, theta_deg):
+    """case 3: source and receiver at the same height, ratio 2 cos(theta)
+    (reference tests/test_DRadiosityFast_infinite_diffuse_plane.py:134-156)"""
+    th = np.deg2rad(theta_deg)
+    source = (2 * np.sin(th), 0.0, 2 * np.cos(th))
+    receiver = (-2 * np.sin(th), 0.0, 2 * np.cos(th))
+    ratio = plane_ratio(source, receiver)
+    assert abs(ratio - 2 * np.cos(th)) <= 0.03 + 0.03 * 2 * np.cos(th)

@@ -307,3 +307,73 @@ def test_diffuse_plane_same_height(plane_ratio, theta_deg):
     receiver = (-2 * np.sin(th), 0.0, 2 * np.cos(th))
     ratio = plane_ratio(source, receiver)
     assert abs(ratio - 2 * np.cos(th)) <= 0.03 + 0.03 * 2 * np.cos(th)
+
+
+# ---------------------------------------------------------------------------
+# whole-pipeline known answers: diffuse room after Kuttruff, reciprocity in a shoebox
+# ---------------------------------------------------------------------------
+def room_etc_oracle(oracle, dims, patch, source, receiver, c, dt, duration, order, absorption):
+    walls = scenes.shoebox(*dims)
+    one = np.array([[[0.0, 0.0, 1.0]]] * len(walls))
+    out = oracle.pipeline(np.array([w[0] for w in walls]), np.array([w[2] for w in walls]),
+                          patch, np.asarray(source, float), np.asarray(receiver, float)[None],
+                          c, dt, duration, order, np.zeros(1), one, one,
+                          np.full((1, 1, 1, 1), 1.0 - absorption), np.zeros(6, np.int64),
+                          brdf_set_before_bake=True)
+    return out["etc_receiver_mono"][0, 0]
+
+
+def room_etc_cuda(dims, patch, source, receiver, c, dt, duration, order, absorption):
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    walls = sp.testing.shoebox_room_stub(*dims)
+    rad = sp.DirectionalRadiosityFast.from_polygon(walls, patch)
+    dirs = pf.Coordinates(0, 0, 1, weights=1)
+    brdf = sp.brdf.create_from_scattering(dirs, dirs, pf.FrequencyData(1, [500]),
+                                          pf.FrequencyData(absorption, [500]))
+    rad.set_wall_brdf(np.arange(len(walls)), brdf, dirs, dirs)
+    rad.set_air_attenuation(pf.FrequencyData(np.zeros(1), [500]))
+    rad.bake_geometry()
+    rad.init_source_energy(pf.Coordinates(*source))
+    rad.calculate_energy_exchange(speed_of_sound=c, etc_time_resolution=dt,
+                                  etc_duration=duration, max_reflection_order=order,
+                                  recalculate=True)
+    return rad.collect_energy_receiver_mono(pf.Coordinates(*receiver)).time[0, 0]
+
+
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def room_etc(request, oracle):
+    if request.param == "oracle":
+        return lambda *a: room_etc_oracle(oracle, *a)
+    return room_etc_cuda
+
+
+def test_diffuse_room_decay_after_kuttruff(room_etc):
+    """reference tests/test_DRadiosityFast_order.py:49-117: perfectly diffuse 5 x 3 x 4 m
+    room, absorption 0.1, 3 orders; bins 5..18 of the ETC within 2 dB of Kuttruff's
+    Eq. 4.10"""
+    x, y, z = 5, 3, 4
+    c, dt, duration, absorption = 346.18, 1 / 500, 0.15, 0.1
+    etc = room_etc((x, y, z), 1.0, (2, 1.5, 2), (3, 1.5, 2), c, dt, duration, 3, absorption)
+    t = np.arange(etc.shape[-1]) * dt
+    surface = 2 * (x * y + x * z + y * z)
+    volume = x * y * z
+    w0 = 4 / (surface * absorption) / volume
+    analytic = w0 * np.exp(c * surface * np.log(1 - absorption) / (4 * volume) * (t - 0.03))
+    got_db, want_db = 10 * np.log10(etc[5:19]), 10 * np.log10(analytic[5:19])
+    assert np.max(np.abs(got_db - want_db)) < 2.0
+
+
+@pytest.mark.parametrize("receiver", [(0.5, 1.0, 2.5), (1.0, 2.5, 1.5)])
+@pytest.mark.parametrize("order", [10, 20])
+@pytest.mark.parametrize("patch", [1.0, 1.5])
+def test_reciprocity_in_a_shoebox(room_etc, receiver, order, patch):
+    """reference tests/test_multisource.py:51-137: swapping source and receiver in a
+    lossless diffuse 3 x 3 x 3 m room gives the same ETC (6 decimals there)"""
+    source = (2.0, 1.5, 1.5)
+    args = ((3, 3, 3), patch)
+    tail = (343.0, 1 / 200, 0.5, order, 0.0)
+    a = room_etc(*args, source, receiver, *tail)
+    b = room_etc(*args, receiver, source, *tail)
+    assert abs(a.sum() - b.sum()) < 1.5e-6
+    assert np.max(np.abs(a - b)) < 1.5e-6

@@ -377,3 +377,21 @@ def test_reciprocity_in_a_shoebox(room_etc, receiver, order, patch):
     b = room_etc(*args, receiver, source, *tail)
     assert abs(a.sum() - b.sum()) < 1.5e-6
     assert np.max(np.abs(a - b)) < 1.5e-6
+
+
+@pytest.mark.parametrize("src", [(2.0, 0, 0), (2.0, 2.0, 0), (2.0, 0.0, 2.0)])
+@pytest.mark.parametrize("rec", [(1.0, 0.0, 0), (2.0, -2.0, 0), (2.0, 0.0, -2.0)])
+def test_source_patch_receiver_reciprocity(oracle, src, rec):
+    """reference tests/test_multisource.py:140-199: for one 2 x 2 m patch the product of
+    the source->patch and patch->receiver point factors is symmetric in source and
+    receiver (6 decimals there).  Oracle only: the CUDA point kernels are pinned to it by
+    the golden point_patch vectors."""
+    patch = np.array([[[0, -1, -1], [0, -1, 1], [0, 1, 1], [0, 1, -1]]], float)
+    centre = patch.mean(axis=1)
+    seen = np.ones(1, np.uint8)
+    energy = []
+    for s_, r_ in ((src, rec), (rec, src)):
+        e_s, _ = oracle.source_energy(np.array(s_, float), centre, patch, seen, np.zeros(1))
+        e_r = oracle.receiver_factor(np.array(r_, float), patch, seen)
+        energy.append(e_s[0, 0] * e_r[0])
+    assert abs(energy[0] - energy[1]) < 1.5e-6 and energy[0] > 0

@@ -143,6 +143,22 @@ int spb_exchange_gather_window(const void *e_prev, void *g, const int64_t *ent_p
                                int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
                                int64_t pad, int64_t window, int dtype, void *stream);
 
+/* Stage 1, tensor-memory variant (FP64 only; same result as spb_exchange_gather, same
+ * records and arguments as spb_exchange_gather_window).  The sender window of a record
+ * is staged by a 2-D TMA tensor load into shared memory and from there into TENSOR
+ * MEMORY with time along the TMEM columns, 16 consecutive bins (+ the delay window) per
+ * TMEM lane; a receiver's delay then is a dynamic column address of tcgen05.ld, which
+ * feeds the FMAs from a datapath three times wider than shared memory.
+ * Replaces the inner loops of _energy_exchange (RadiosityFast.py:1121-1144).  e_prev
+ * must be the base of the whole (n_bands * n_alloc * n_dirs, ld) histogram, 16-byte
+ * aligned. */
+int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr,
+                             const void *recs, const int32_t *cta_order,
+                             int64_t n_patches, int64_t n_alloc, int64_t n_classes,
+                             int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi,
+                             int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
+                             int64_t pad, int64_t window, int dtype, void *stream);
+
 /* Stage 2 of one order for receiver patches [j_lo, j_hi), bands [b_lo, b_hi): BRDF
  * contraction, writes e_cur rows of those patches and accumulates them into
  * e_total.  coef: [C, D, B] in dtype. */

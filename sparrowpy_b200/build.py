@@ -22,6 +22,7 @@ SOURCES = [
     ("exchange.cu", []),
     ("exchange_tma.cu", []),
     ("exchange_win.cu", []),
+    ("exchange_tmem.cu", []),
     ("bake.cu", ["--fmad=false"]),
 ]
 

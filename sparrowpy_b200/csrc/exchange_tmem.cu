@@ -1,0 +1,486 @@
+// Stage 1 of the energy exchange with the sender window held in TENSOR MEMORY
+// (sm_100a, FP64).
+//
+//   G[c,j,b,t] = sum_{i -> j in class c} ff * E_prev[src(i), b, t - delay]
+//   (reference RadiosityFast.py:1124-1143, one reflection order)
+//
+// Why: every FMA of this sum needs one operand from a *shifted* sender row, and the
+// shift (the pair's delay bin) differs per (sender, receiver).  Read from shared memory
+// that is one 8-byte operand per FMA at 128 B/clk/SM = a quarter of the FP64 pipe
+// (k_gather_tma, measured 79 % of that roof).  Registers cannot be indexed dynamically,
+// so a register window needs a branch per (record, receiver) (k_gather_win, no faster).
+// Tensor memory can: tcgen05.ld takes a *dynamic column address* and returns consecutive
+// columns of the thread's TMEM lane in statically named registers, and it is a separate
+// datapath (measured on B200: 360-400 B/clk/SM with 8 warps, tools/microbench).  So the
+// window lives in TMEM with time along the columns, and a delay is a column offset.
+//
+// Layout ("Toeplitz rows"): a CTA covers 8 receivers x 2048 time bins; TMEM lane R holds,
+// for the record in flight, the contiguous energies E[T0(R) - dbase - H .. T0(R) - dbase
+// + 16) of the sender row, T0(R) = first of the 16 consecutive bins the lane owns, H = the
+// widest delay window of a record.  A receiver whose delay is dbase + rel reads its 16
+// operands with two tcgen05.ld.32x32b.x16 at column 2 (H - rel).
+//
+// Pipeline per record (one (tile, sender row, delay window), 80 bytes, the records of
+// exchange.build_window_records):
+//   producer warp : one 2-D TMA tensor load (rows of 16 doubles, SWIZZLE_128B) of the
+//                   sender window + a bulk copy of the record into a shared-memory stage
+//   4 fill warps  : (one per TMEM lane quarter) read the lane's row from the swizzled
+//                   stage with conflict-free LDS.128 (the swizzle makes the 128-byte lane
+//                   pitch hit 8 different bank groups) and write it with tcgen05.st into a
+//                   ring of TMEM stages; they also hand the weights to the consumers
+//   8 consumer warps: (quarter q, receiver group g) 16 bins x 4 receivers per thread =
+//                   64 FP64 accumulators; per receiver 2 tcgen05.ld + 16 DFMA.
+// Quarters run decoupled (per-quarter mbarriers).  Registers are re-balanced with
+// setmaxnreg (consumers 192, fill 88, producer 40).
+//
+// When the histogram is shorter than 2048 bins the four lane quarters are spread over
+// several bands instead (same records, other energy rows), so no lane idles.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace spb {
+namespace tmg {
+
+constexpr int kR = 8;                          // receivers per tile
+constexpr int kLaneT = 16;                     // consecutive time bins per TMEM lane
+constexpr int kQuarterT = 32 * kLaneT;         // 512 bins per lane quarter
+constexpr int kSmemStages = 4;
+constexpr int kBoxArea = 20480;                // bytes reserved for the staged boxes
+constexpr int kStageBytes = 21504;             // box area + record, multiple of 1024
+constexpr int kRecSlot = 96;                   // bytes per (TMEM stage, quarter) record copy
+constexpr int kThreads = 512;
+constexpr int kRegsConsumer = 192, kRegsFill = 88, kRegsProducer = 40;
+
+struct alignas(16) WinRecord {
+    double w[kR];        // weight per receiver slot
+    uint8_t rel[kR];     // delay - dbase (0..H), 255 = no pair in this slot
+    int32_t src;         // sender row = patch * D + outgoing direction
+    int32_t dbase;       // even
+};
+static_assert(sizeof(WinRecord) == 80, "record layout");
+
+template <int H>
+struct Cfg {
+    static constexpr int kRowD = kLaneT + H;           // doubles per TMEM lane row
+    static constexpr int kChunks = kRowD / 2;          // 16-byte chunks per row
+    static constexpr int kCols = 2 * kRowD;            // 32-bit TMEM columns per stage
+    static constexpr int kTmemStages = 512 / kCols;
+    static_assert(H % 2 == 0 && kRowD % 2 == 0, "rows are made of 16-byte chunks");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// both halves of a lane's 16 operands: two loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t (&r)[32], uint32_t addr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
+        "%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+          "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr));
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
+        "%14,%15}, [%16];"
+        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr + 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
+        "%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(addr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
+        "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+        "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+        "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
+        "%14,%15,%16};" ::"r"(addr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
+        "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+                 "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t addr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_store_row(uint32_t addr, const uint32_t *r) {
+    // N 32-bit columns as the fewest power-of-two stores
+    int done = 0;
+    if constexpr (N >= 32) { tmem_st32(addr, r); done = 32; }
+    if constexpr ((N - (N >= 32 ? 32 : 0)) >= 16) { tmem_st16(addr + done, r + done); done += 16; }
+    if constexpr (((N % 16) >= 8)) { tmem_st8(addr + done, r + done); done += 8; }
+    if constexpr (((N % 8) >= 4)) { tmem_st4(addr + done, r + done); done += 4; }
+    static_assert(N % 4 == 0 && N < 64, "row width");
+}
+
+template <int H>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
+              const int64_t *__restrict__ ent_ptr, const WinRecord *__restrict__ recs,
+              const int32_t *__restrict__ cta_order, int64_t n_patches, int64_t n_alloc,
+              int64_t n_blocks, int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t jb_lo,
+              int64_t n_jb, int64_t n_classes, int64_t t_pad, int64_t ld, int64_t pad, int qpb,
+              int n_tchunks) {
+    using C = Cfg<H>;
+    constexpr int TS = C::kTmemStages;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *stages = smem_raw;
+    unsigned char *rec_slots = smem_raw + kSmemStages * kStageBytes;       // [TS][4][kRecSlot]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(rec_slots + TS * 4 * kRecSlot);
+    uint64_t *smem_full = bars;                       // [kSmemStages]
+    uint64_t *smem_empty = smem_full + kSmemStages;   // [kSmemStages]
+    uint64_t *tmem_full = smem_empty + kSmemStages;   // [TS][4]
+    uint64_t *tmem_empty = tmem_full + TS * 4;        // [TS][4]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + TS * 4);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    // ---- which tile, which bands / time chunk ----
+    const int64_t pos = blockIdx.x;
+    const int64_t loc = cta_order ? cta_order[pos] : pos;
+    const int64_t c = loc / n_jb;
+    const int64_t jb = jb_lo + (loc - c * n_jb);
+    const int64_t tile = c * n_blocks + jb;
+    const int64_t e0 = ent_ptr[tile], e1 = ent_ptr[tile + 1];
+    if (e0 == e1) return;                              // no pairs: rows are never read
+    const int bands_per_cta = 4 / qpb;
+    const int64_t bg = blockIdx.y / n_tchunks;
+    const int64_t tc = blockIdx.y - bg * n_tchunks;
+    const int64_t band0 = b_lo + bg * bands_per_cta;
+    const int64_t t_base = tc * (int64_t)kQuarterT * qpb;   // first bin of the CTA's chunk
+    // quarter q: band band0 + q / qpb, bins [t_base + (q % qpb) * 512, + 512)
+    auto q_band = [&](int q) { return band0 + q / qpb; };
+    auto q_t0 = [&](int q) { return t_base + (int64_t)(q % qpb) * kQuarterT; };
+    auto q_active = [&](int q) { return q_band(q) < b_hi && q_t0(q) < t_pad; };
+    int n_act_q = 0, n_act_bands = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) n_act_q += q_active(q) ? 1 : 0;
+    for (int s = 0; s < bands_per_cta; ++s) n_act_bands += (band0 + s < b_hi) ? 1 : 0;
+    const int box_rows = 32 * qpb + 2;
+    const int box_stride = (box_rows * 128 + 1023) & ~1023;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSmemStages; ++s) {
+            mbar_init(&smem_full[s], 1);
+            mbar_init(&smem_empty[s], n_act_q);
+        }
+        for (int s = 0; s < TS * 4; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+            smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 12) {
+        // ---------------- producer warpgroup (one working lane) ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        if (warp == 12) {
+            const uint32_t tx_bytes = (uint32_t)(n_act_bands * box_rows * 128 + sizeof(WinRecord));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t e = e0; e < e1; e += 32) {
+                int32_t s = 0, db = 0;
+                if (e + lane < e1) { s = recs[e + lane].src; db = recs[e + lane].dbase; }
+                const int cnt = (int)min((int64_t)32, e1 - e);
+                for (int k = 0; k < cnt; ++k) {
+                    const int32_t sk = __shfl_sync(0xffffffffu, s, k);
+                    const int32_t dk = __shfl_sync(0xffffffffu, db, k);
+                    if (lane == 0) {
+                        mbar_wait(&smem_empty[stage], phase ^ 1);
+                        mbar_expect_tx(&smem_full[stage], tx_bytes);
+                        unsigned char *st = stages + (size_t)stage * kStageBytes;
+                        for (int bs = 0; bs < n_act_bands; ++bs) {
+                            // first double of lane 0's row; >> 4 = tensor row (floor)
+                            const int64_t a0 = ((band0 + bs) * n_alloc * n_dirs + sk) * ld + pad +
+                                               t_base - dk - H;
+                            const int32_t row0 = (int32_t)(a0 >> 4);
+                            asm volatile(
+                                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                                "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(st + bs * box_stride)),
+                                "l"(&tmap), "r"(0), "r"(row0), "r"(smem_u32(&smem_full[stage]))
+                                : "memory");
+                        }
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                            ::"r"(smem_u32(st + kBoxArea)), "l"(recs + e + k),
+                            "r"((uint32_t)sizeof(WinRecord)), "r"(smem_u32(&smem_full[stage]))
+                            : "memory");
+                    }
+                    if (++stage == kSmemStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ---------------- fill warps: smem stage -> TMEM stage ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsFill));
+        const int q = warp - 8;
+        if (q_active(q)) {
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int rb = (q % qpb) * 32 + lane;           // the lane's row inside its box
+            const int box_off = (q / qpb) * box_stride;
+            int ss = 0, ts = 0;
+            uint32_t sphase = 0, tphase = 0;
+            for (int64_t e = e0; e < e1; ++e) {
+                mbar_wait(&smem_full[ss], sphase);
+                const unsigned char *st = stages + (size_t)ss * kStageBytes;
+                const WinRecord *rec = reinterpret_cast<const WinRecord *>(st + kBoxArea);
+                // 16-byte chunk at which lane 0's row starts inside its first tensor row
+                const int joff = (int)(((uint32_t)(-(rec->dbase + H))) & 15u) >> 1;
+                uint32_t v[C::kCols];
+#pragma unroll
+                for (int ch = 0; ch < C::kChunks; ++ch) {
+                    const int lc = ch + joff;
+                    const int row = rb + (lc >> 3);
+                    const int chunk = (lc & 7) ^ (row & 7);
+                    const uint4 x = *reinterpret_cast<const uint4 *>(st + box_off + row * 128 +
+                                                                     chunk * 16);
+                    v[4 * ch] = x.x; v[4 * ch + 1] = x.y; v[4 * ch + 2] = x.z; v[4 * ch + 3] = x.w;
+                }
+                // the record (weights, shifts) travels with the TMEM stage
+                uint64_t rec_word = 0;
+                if (lane < 10) rec_word = reinterpret_cast<const uint64_t *>(rec)[lane];
+                mbar_wait(&tmem_empty[ts * 4 + q], tphase ^ 1);
+                tc_fence_after();
+                tmem_store_row<C::kCols>(trow + (uint32_t)(ts * C::kCols), v);
+                if (lane < 10)
+                    reinterpret_cast<uint64_t *>(rec_slots + (ts * 4 + q) * kRecSlot)[lane] = rec_word;
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&smem_empty[ss]);
+                    mbar_arrive(&tmem_full[ts * 4 + q]);
+                }
+                if (++ss == kSmemStages) { ss = 0; sphase ^= 1; }
+                if (++ts == TS) { ts = 0; tphase ^= 1; }
+            }
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
+        const int q = warp & 3, grp = warp >> 2;
+        if (q_active(q)) {
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            double acc[4][kLaneT];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int k = 0; k < kLaneT; ++k) acc[s][k] = 0.0;
+            int ts = 0;
+            uint32_t tphase = 0;
+            for (int64_t e = e0; e < e1; ++e) {
+                mbar_wait(&tmem_full[ts * 4 + q], tphase);
+                tc_fence_after();
+                const unsigned char *slot = rec_slots + (ts * 4 + q) * kRecSlot;
+                const double2 w01 = *reinterpret_cast<const double2 *>(slot + 32 * grp);
+                const double2 w23 = *reinterpret_cast<const double2 *>(slot + 32 * grp + 16);
+                const uint32_t rel4 = *reinterpret_cast<const uint32_t *>(slot + 64 + 4 * grp);
+                const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+                const uint32_t tstage = trow + (uint32_t)(ts * C::kCols + 2 * H);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const uint32_t r = (rel4 >> (8 * s)) & 0xffu;
+                    if (r != 255u) {                                   // warp-uniform
+                        uint32_t x[32];
+                        tmem_ld16x2(x, tstage - 2 * r);
+#pragma unroll
+                        for (int k = 0; k < kLaneT; ++k)
+                            acc[s][k] = fma(w[s], __hiloint2double((int)x[2 * k + 1], (int)x[2 * k]),
+                                            acc[s][k]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[ts * 4 + q]);
+                if (++ts == TS) { ts = 0; tphase ^= 1; }
+            }
+            // ---- epilogue: 16 consecutive bins per receiver row ----
+            const int64_t b = q_band(q);
+            const int64_t t0 = q_t0(q) + (int64_t)lane * kLaneT;
+            if (t0 < t_pad) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int64_t j = jb * kR + grp * 4 + s;
+                    if (j < n_patches) {
+                        double2 *out = reinterpret_cast<double2 *>(
+                            g + ((b * n_classes + c) * n_patches + j) * ld + pad + t0);
+#pragma unroll
+                        for (int k = 0; k < kLaneT / 2; ++k)
+                            out[k] = make_double2(acc[s][2 * k], acc[s][2 * k + 1]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+}
+
+typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiled encode_fn() {
+    static EncodeTiled fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult qres;
+        void *p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+                cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiled)p;
+    }
+    return fn;
+}
+
+template <int H>
+int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRecord *recs,
+           const int32_t *cta_order, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
+           int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+           int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, cudaStream_t st) {
+    using C = Cfg<H>;
+    const int64_t n_blocks = ceil_div(n_patches, kR);
+    const int64_t jb_lo = j_lo / kR, jb_hi = ceil_div(j_hi, kR);
+    const int64_t n_jb = jb_hi - jb_lo;
+    const int64_t n_tiles = n_classes * n_jb;
+    if (n_tiles == 0 || b_hi == b_lo) return 0;
+    SPB_REQUIRE(n_tiles <= 2147483647LL, "too many tiles for one launch");
+    SPB_REQUIRE(ld % 16 == 0 && pad % 16 == 0, "row pitch must be a multiple of 16 bins");
+    SPB_REQUIRE(pad >= H + 16, "pad smaller than the delay window");
+    // quarters per band: 512-bin units of one band a CTA covers (the rest of its four
+    // lane quarters go to further bands)
+    const int64_t units = ceil_div(t_pad, (int64_t)kQuarterT);
+    const int qpb = units >= 4 ? 4 : (units >= 2 ? 2 : 1);
+    const int n_tchunks = (int)ceil_div(units, (int64_t)qpb);
+    const int bands_per_cta = 4 / qpb;
+    const int64_t n_bgroups = ceil_div(b_hi - b_lo, (int64_t)bands_per_cta);
+    SPB_REQUIRE(n_bgroups * n_tchunks <= 65535, "too many band groups x time chunks");
+
+    EncodeTiled encode = encode_fn();
+    if (!encode) return fail(-2, "cuTensorMapEncodeTiled", "driver entry point not found");
+    const int64_t total = n_bands * n_alloc * n_dirs * ld;             // doubles in e_prev
+    SPB_REQUIRE(total / 16 <= 2147483647LL, "histogram too large for 32-bit tensor rows");
+    CUtensorMap tmap;
+    cuuint64_t dims[2] = {16, (cuuint64_t)(total / 16)};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {16, (cuuint32_t)(32 * qpb + 2)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)e_prev, dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled", "encode failed");
+
+    const size_t smem = (size_t)kSmemStages * kStageBytes + (size_t)C::kTmemStages * 4 * kRecSlot +
+                        (2 * kSmemStages + 8 * C::kTmemStages) * sizeof(uint64_t) + 16;
+    SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    dim3 grid((unsigned)n_tiles, (unsigned)(n_bgroups * n_tchunks));
+    k_gather_tmem<H><<<grid, kThreads, smem, st>>>(tmap, g, ent_ptr, recs, cta_order, n_patches,
+                                                   n_alloc, n_blocks, n_dirs, b_lo, b_hi, jb_lo,
+                                                   n_jb, n_classes, t_pad, ld, pad, qpb,
+                                                   n_tchunks);
+    return check_launch("k_gather_tmem");
+}
+
+}  // namespace tmg
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" {
+
+int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr,
+                             const void *recs, const int32_t *cta_order, int64_t n_patches,
+                             int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
+                             int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+                             int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad,
+                             int64_t window, int dtype, void *stream) {
+    SPB_REQUIRE(e_prev && g && ent_ptr, "null pointer");
+    SPB_REQUIRE(dtype == SPB_F64, "the tensor-memory gather is FP64 only");
+    SPB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= n_patches, "receiver range");
+    SPB_REQUIRE(0 <= b_lo && b_lo <= b_hi && b_hi <= n_bands, "band range");
+    SPB_REQUIRE(n_alloc >= n_patches, "n_alloc < n_patches");
+    SPB_REQUIRE(j_lo == j_hi || j_lo % tmg::kR == 0,
+                "j_lo must be a multiple of the receiver tile (8)");
+    SPB_REQUIRE(t_pad % 256 == 0 && ld == pad + t_pad, "layout (use spb_exchange_layout)");
+    SPB_REQUIRE(((uintptr_t)e_prev & 15) == 0, "e_prev must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *ep = (const double *)e_prev;
+    const tmg::WinRecord *r = (const tmg::WinRecord *)recs;
+    if (window == 4)
+        return tmg::launch<4>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc, n_classes,
+                             n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
+    if (window == 10)
+        return tmg::launch<10>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
+                              n_classes, n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad,
+                              st);
+    return fail(-1, "invalid argument", "window must be 4 or 10");
+}
+
+}  // extern "C"

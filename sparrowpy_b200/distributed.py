@@ -34,7 +34,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .exchange import EnergyHistogram, gather_kind, window_arg
+from .exchange import EnergyHistogram, launch_gather
 
 SHARD_ALIGN = 8
 
@@ -117,23 +117,8 @@ class ShardedExchange:
 
     # -- local kernels -------------------------------------------------------
     def _cuda_order(self, prev, cur, total, b_lo, b_hi):
-        t = self.t
-        code = _lib.I32(t.dtype)
-        st = _lib.stream_ptr()
-        kind = gather_kind()
-        if t.win_recs is not None and kind != "csr":
-            _lib.call("spb_exchange_gather_window", prev, self.g, t.win_ptr, t.win_recs,
-                      self.cta_order(), t.n_patches, self.n_alloc, t.n_classes, t.n_dirs,
-                      t.n_bands, b_lo, b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld,
-                      self.pad, window_arg(t), code, st)
-        elif t.recs is not None and kind != "csr":
-            _lib.call("spb_exchange_gather_tiled", prev, self.g, t.ent_ptr, t.recs,
-                      self.cta_order(), t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
-                      b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad, code, st)
-        else:
-            _lib.call("spb_exchange_gather", prev, self.g, t.seg_ptr, t.src, t.wgt, t.dly,
-                      t.n_patches, self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo,
-                      b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad, code, st)
+        launch_gather(self.t, prev, self.g, self.cta_order(), self.n_alloc, b_lo, b_hi,
+                      self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad)
         self._mix(cur, total, b_lo, b_hi)
 
     def cta_order(self):

@@ -82,15 +82,19 @@ def directed_pairs(pairs, ff_pairs, areas):
 
 
 def gather_kind(code=None):
-    """Stage-1 kernel selected by ``SPB_GATHER``: ``tma`` (default; bucket records,
-    exchange_tma.cu), ``win`` (register-window records, exchange_win.cu; FP64 only,
-    FP32 tables fall back to ``tma``) or ``csr`` (cross-check kernel)."""
-    kind = os.environ.get("SPB_GATHER", "tma")
-    if kind not in ("tma", "win", "csr"):
-        raise ValueError(f"SPB_GATHER={kind!r}: use tma, win or csr")
-    if kind == "win" and code is not None and code != _lib.F64:
+    """Stage-1 kernel selected by ``SPB_GATHER``: ``tmem`` (window records, operands from
+    tensor memory, exchange_tmem.cu; FP64 only), ``tma`` (bucket records, operands from
+    shared memory, exchange_tma.cu), ``win`` (register-window records, exchange_win.cu;
+    FP64 only) or ``csr`` (cross-check kernel).  FP32 tables fall back to ``tma``."""
+    kind = os.environ.get("SPB_GATHER", DEFAULT_GATHER)
+    if kind not in ("tmem", "tma", "win", "csr"):
+        raise ValueError(f"SPB_GATHER={kind!r}: use tmem, tma, win or csr")
+    if kind in ("win", "tmem") and code is not None and code != _lib.F64:
         kind = "tma"
     return kind
+
+
+DEFAULT_GATHER = "tma"
 
 
 def window_arg(tables):
@@ -98,11 +102,37 @@ def window_arg(tables):
     tuning variant selected by the environment -- +100: 4 instead of 8 time bins per
     lane (``SPB_WIN_LANE_T=4``); +200 / +300: variants 2 and 3, row copied by one warp per
     record and jump-table dispatch per receiver / chained per record
-    (``SPB_WIN_VARIANT=2|3``; compiled but not yet run on a GPU)."""
+    (``SPB_WIN_VARIANT=2|3``)."""
     variant = os.environ.get("SPB_WIN_VARIANT", "1")
     if variant in ("2", "3"):
         return tables.win_w + 100 * int(variant)
     return tables.win_w + (100 if os.environ.get("SPB_WIN_LANE_T", "8") == "4" else 0)
+
+
+def launch_gather(tables, prev, g, cta_order, n_alloc, b_lo, b_hi, j_lo, j_hi, t_pad, ld,
+                  pad, kind=None):
+    """Stage 1 of one order (``G`` from ``E_{k-1}``) with the kernel the tables were
+    built for: receivers [j_lo, j_hi), bands [b_lo, b_hi)."""
+    t = tables
+    code, st = _lib.I32(t.dtype), _lib.stream_ptr()
+    kind = kind or gather_kind(t.dtype)
+    if t.win_recs is not None and kind != "csr":
+        if kind == "tmem":
+            _lib.call("spb_exchange_gather_tmem", prev, g, t.win_ptr, t.win_recs, cta_order,
+                      t.n_patches, n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
+                      j_lo, j_hi, t_pad, ld, pad, t.win_w, code, st)
+        else:
+            _lib.call("spb_exchange_gather_window", prev, g, t.win_ptr, t.win_recs, cta_order,
+                      t.n_patches, n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
+                      j_lo, j_hi, t_pad, ld, pad, window_arg(t), code, st)
+    elif t.recs is not None and kind != "csr":
+        _lib.call("spb_exchange_gather_tiled", prev, g, t.ent_ptr, t.recs, cta_order,
+                  t.n_patches, n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, j_lo,
+                  j_hi, t_pad, ld, pad, code, st)
+    else:
+        _lib.call("spb_exchange_gather", prev, g, t.seg_ptr, t.src, t.wgt, t.dly, t.n_patches,
+                  n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, j_lo, j_hi, t_pad,
+                  ld, pad, code, st)
 
 
 def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches,
@@ -154,7 +184,7 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     gather = gather or gather_kind(code)
     ent_ptr = recs = win_ptr = win_recs = None
     win_w = 0
-    if gather == "win" and code == _lib.F64:
+    if gather in ("win", "tmem") and code == _lib.F64:
         win_ptr, win_recs, win_w = build_window_records(
             sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs, n_classes, code)
     else:

@@ -18,7 +18,7 @@ sys.path.insert(0, REPO)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c4")
-    ap.add_argument("--gather", default="win", choices=["tma", "win", "csr"])
+    ap.add_argument("--gather", default="win", choices=["tma", "tmem", "win", "csr"])
     ap.add_argument("--orders", type=int, default=4)
     args = ap.parse_args()
     os.environ["SPB_GATHER"] = args.gather

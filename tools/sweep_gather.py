@@ -6,7 +6,7 @@ the default kernel.
 
     python tools/sweep_gather.py --config c4 [--orders 3] [--variants tma,win,win-v2,...]
 
-Variants: tma | csr | win (variant 1) | win-lt4 | win-v2 | win-v3, each optionally with
+Variants: tma | tmem | csr | win (variant 1) | win-lt4 | win-v2 | win-v3, each optionally with
 `@a4` = sector-aligned rows (SPB_WIN_ALIGN=4), e.g. `win-v3@a4`.  Unverified variants
 are run in this process: wrap the call in `timeout`."""
 import argparse
@@ -19,6 +19,7 @@ sys.path.insert(0, REPO)
 
 ENV = {
     "tma": dict(SPB_GATHER="tma"),
+    "tmem": dict(SPB_GATHER="tmem"),
     "csr": dict(SPB_GATHER="csr"),
     "win": dict(SPB_GATHER="win"),
     "win-lt4": dict(SPB_GATHER="win", SPB_WIN_LANE_T="4"),
@@ -32,7 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c4")
     ap.add_argument("--orders", type=int, default=3)
-    ap.add_argument("--variants", default="tma,win,win@a4,win-v2,win-v2@a4,win-v3,win-v3@a4")
+    ap.add_argument("--variants", default="tma,tmem,win-v3")
     args = ap.parse_args()
     import torch
     import bench
@@ -62,24 +63,10 @@ def main():
 
         def gather_only(prev, cur, total, b_lo, b_hi, sx=sx, tables=tables):
             t = tables
-            c32, sp = _lib.I32(t.dtype), _lib.stream_ptr()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             ev[0].record()
-            kind = exchange.gather_kind()
-            if t.win_recs is not None and kind != "csr":
-                _lib.call("spb_exchange_gather_window", prev, sx.g, t.win_ptr, t.win_recs,
-                          sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs,
-                          t.n_bands, b_lo, b_hi, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad,
-                          exchange.window_arg(t), c32, sp)
-            elif kind != "csr":
-                _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
-                          sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs,
-                          t.n_bands, b_lo, b_hi, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32,
-                          sp)
-            else:
-                _lib.call("spb_exchange_gather", prev, sx.g, t.seg_ptr, t.src, t.wgt, t.dly,
-                          t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
-                          sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32, sp)
+            exchange.launch_gather(t, prev, sx.g, sx.cta_order(), sx.n_alloc, b_lo, b_hi,
+                                   sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad)
             ev[1].record()
             events.append(ev)
             sx._mix(cur, total, b_lo, b_hi)

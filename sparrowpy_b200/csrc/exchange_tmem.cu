@@ -31,11 +31,12 @@
 //   8 consumer warps: (quarter q, receiver group g) 16 bins x 4 receivers per thread =
 //                   64 FP64 accumulators; per receiver 2 tcgen05.ld + 16 DFMA.
 // Quarters run decoupled (per-quarter mbarriers).  Registers are re-balanced with
-// setmaxnreg (consumers 192, fill 88, producer 40).
+// setmaxnreg (consumers 184, fill 104, producer 40).
 //
 // When the histogram is shorter than 2048 bins the four lane quarters are spread over
 // several bands instead (same records, other energy rows), so no lane idles.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -45,12 +46,13 @@ namespace tmg {
 constexpr int kR = 8;                          // receivers per tile
 constexpr int kLaneT = 16;                     // consecutive time bins per TMEM lane
 constexpr int kQuarterT = 32 * kLaneT;         // 512 bins per lane quarter
-constexpr int kSmemStages = 4;
+constexpr int kSmemStages = 8;
 constexpr int kBoxArea = 20480;                // bytes reserved for the staged boxes
 constexpr int kStageBytes = 21504;             // box area + record, multiple of 1024
 constexpr int kRecSlot = 96;                   // bytes per (TMEM stage, quarter) record copy
-constexpr int kThreads = 512;
-constexpr int kRegsConsumer = 192, kRegsFill = 88, kRegsProducer = 40;
+constexpr int kThreads = 512;   // 8 consumer + 4 fill + 1 producer (+ 3 idle) warps; 512 x 128 regs
+                                // at launch = the whole file, so setmaxnreg only re-deals it
+constexpr int kRegsConsumer = 184, kRegsFill = 104, kRegsProducer = 40;
 
 struct alignas(16) WinRecord {
     double w[kR];        // weight per receiver slot
@@ -59,6 +61,10 @@ struct alignas(16) WinRecord {
     int32_t dbase;       // even
 };
 static_assert(sizeof(WinRecord) == 80, "record layout");
+// setmaxnreg.inc can only take what setmaxnreg.dec released inside the CTA (a pool that starts
+// empty): the re-deal must not need more registers than the launch allocated
+static_assert(8 * kRegsConsumer + 4 * kRegsFill + 4 * kRegsProducer <= 16 * 128,
+              "register re-deal exceeds the launch allocation (the kernel would hang)");
 
 template <int H>
 struct Cfg {
@@ -107,8 +113,9 @@ __device__ __forceinline__ void tc_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// both halves of a lane's 16 operands: two loads in flight, one wait
-__device__ __forceinline__ void tmem_ld16x2(uint32_t (&r)[32], uint32_t addr) {
+// 16 consecutive 32-bit columns (8 doubles) of this thread's TMEM lane; asynchronous:
+// tcgen05.wait::ld before the registers are read
+__device__ __forceinline__ void tmem_ld16(uint32_t *r, uint32_t addr) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
         "%14,%15}, [%16];"
@@ -116,14 +123,6 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t (&r)[32], uint32_t addr) {
           "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
           "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(addr));
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
-        "%14,%15}, [%16];"
-        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(addr + 16));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t *r) {
     asm volatile(
@@ -167,6 +166,81 @@ __device__ __forceinline__ void tmem_store_row(uint32_t addr, const uint32_t *r)
     static_assert(N % 4 == 0 && N < 64, "row width");
 }
 
+// ---- raw shared-memory / mbarrier accessors on 32-bit shared addresses (no generic
+// address arithmetic in the inner loops)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_f64x2(double &a, double &b, uint32_t addr) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
+// One record of the fill: lane `rb`'s row (C::kChunks 16-byte chunks starting at logical
+// chunk J of its first tensor row) from the swizzled stage into the TMEM stage.  p[j] =
+// address of the lane's tensor row j with the row's swizzle key folded in, so that logical
+// chunk cc of that row is at p[j] ^ (cc << 4).
+// The lane's whole row through the registers at once: all LDS.128 are independent (one
+// shared-memory latency per record), then the fewest power-of-two tcgen05.st.
+template <int H, int J>
+__device__ __forceinline__ void fill_row(const uint32_t (&p)[3], uint32_t taddr) {
+    using C = Cfg<H>;
+    uint32_t v[C::kCols];
+#pragma unroll
+    for (int i = 0; i < C::kChunks; ++i) {
+        const int lc = i + J;
+        const uint4 x = lds128(p[lc >> 3] ^ (uint32_t)((lc & 7) << 4));
+        v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    }
+    tmem_store_row<C::kCols>(taddr, v);
+}
+
 template <int H>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
@@ -174,18 +248,19 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
               const int32_t *__restrict__ cta_order, int64_t n_patches, int64_t n_alloc,
               int64_t n_blocks, int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t jb_lo,
               int64_t n_jb, int64_t n_classes, int64_t t_pad, int64_t ld, int64_t pad, int qpb,
-              int n_tchunks) {
+              int n_tchunks, int dbg) {
     using C = Cfg<H>;
     constexpr int TS = C::kTmemStages;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *stages = smem_raw;
-    unsigned char *rec_slots = smem_raw + kSmemStages * kStageBytes;       // [TS][4][kRecSlot]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(rec_slots + TS * 4 * kRecSlot);
-    uint64_t *smem_full = bars;                       // [kSmemStages]
-    uint64_t *smem_empty = smem_full + kSmemStages;   // [kSmemStages]
-    uint64_t *tmem_full = smem_empty + kSmemStages;   // [TS][4]
-    uint64_t *tmem_empty = tmem_full + TS * 4;        // [TS][4]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + TS * 4);
+    // layout: kSmemStages x kStageBytes | rec slots [TS][4][kRecSlot] | barriers | tmem slot
+    const uint32_t sm_stages = smem_u32(smem_raw);
+    const uint32_t sm_slots = sm_stages + kSmemStages * kStageBytes;
+    const uint32_t sm_full = sm_slots + TS * 4 * kRecSlot;           // smem_full[kSmemStages]
+    const uint32_t sm_empty = sm_full + 8 * kSmemStages;              // smem_empty[kSmemStages]
+    const uint32_t tm_full = sm_empty + 8 * kSmemStages;              // tmem_full[TS][4]
+    const uint32_t tm_empty = tm_full + 8 * TS * 4;                   // tmem_empty[TS][4]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(
+        smem_raw + kSmemStages * kStageBytes + TS * 4 * kRecSlot + 16 * kSmemStages + 64 * TS);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -196,8 +271,9 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
     const int64_t c = loc / n_jb;
     const int64_t jb = jb_lo + (loc - c * n_jb);
     const int64_t tile = c * n_blocks + jb;
-    const int64_t e0 = ent_ptr[tile], e1 = ent_ptr[tile + 1];
-    if (e0 == e1) return;                              // no pairs: rows are never read
+    const int64_t e0 = ent_ptr[tile];
+    const int n_rec = (int)(ent_ptr[tile + 1] - e0);
+    if (n_rec == 0) return;                            // no pairs: rows are never read
     const int bands_per_cta = 4 / qpb;
     const int64_t bg = blockIdx.y / n_tchunks;
     const int64_t tc = blockIdx.y - bg * n_tchunks;
@@ -216,12 +292,13 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSmemStages; ++s) {
-            mbar_init(&smem_full[s], 1);
-            mbar_init(&smem_empty[s], n_act_q);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_full + 8 * s), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_empty + 8 * s),
+                         "r"(n_act_q));
         }
         for (int s = 0; s < TS * 4; ++s) {
-            mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 2);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tm_full + 8 * s), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tm_empty + 8 * s), "r"(2));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -236,42 +313,45 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= 12) {
-        // ---------------- producer warpgroup (one working lane) ----------------
+        // ---------------- producer warp (one working lane) ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
-        if (warp == 12) {
-            const uint32_t tx_bytes = (uint32_t)(n_act_bands * box_rows * 128 + sizeof(WinRecord));
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t e = e0; e < e1; e += 32) {
-                int32_t s = 0, db = 0;
-                if (e + lane < e1) { s = recs[e + lane].src; db = recs[e + lane].dbase; }
-                const int cnt = (int)min((int64_t)32, e1 - e);
-                for (int k = 0; k < cnt; ++k) {
-                    const int32_t sk = __shfl_sync(0xffffffffu, s, k);
-                    const int32_t dk = __shfl_sync(0xffffffffu, db, k);
-                    if (lane == 0) {
-                        mbar_wait(&smem_empty[stage], phase ^ 1);
-                        mbar_expect_tx(&smem_full[stage], tx_bytes);
-                        unsigned char *st = stages + (size_t)stage * kStageBytes;
-                        for (int bs = 0; bs < n_act_bands; ++bs) {
-                            // first double of lane 0's row; >> 4 = tensor row (floor)
-                            const int64_t a0 = ((band0 + bs) * n_alloc * n_dirs + sk) * ld + pad +
-                                               t_base - dk - H;
-                            const int32_t row0 = (int32_t)(a0 >> 4);
-                            asm volatile(
-                                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-                                "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(st + bs * box_stride)),
-                                "l"(&tmap), "r"(0), "r"(row0), "r"(smem_u32(&smem_full[stage]))
-                                : "memory");
-                        }
+        const uint32_t tx_bytes = (uint32_t)(n_act_bands * box_rows * 128 + sizeof(WinRecord));
+        // first double of lane 0's row = a_base + band slot * a_band + src * ld - dbase
+        const int64_t a_band = n_alloc * n_dirs * ld;
+        const int64_t a_base = band0 * a_band + pad + t_base - H;
+        const WinRecord *rp = recs + e0;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int e = 0; e < (warp == 12 ? n_rec : 0); e += 32) {    // warps 13..15 idle
+            int32_t s = 0, db = 0;
+            if (e + lane < n_rec) { s = rp[e + lane].src; db = rp[e + lane].dbase; }
+            const int cnt = min(32, n_rec - e);
+            for (int k = 0; k < cnt; ++k) {
+                const int32_t sk = __shfl_sync(0xffffffffu, s, k);
+                const int32_t dk = __shfl_sync(0xffffffffu, db, k);
+                if (lane == 0) {
+                    mbar_wait_a(sm_empty + 8 * stage, phase ^ 1);
+                    const uint32_t bar = sm_full + 8u * stage;
+                    const uint32_t st = sm_stages + (uint32_t)stage * kStageBytes;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                                 "r"((dbg & 8) ? (uint32_t)sizeof(WinRecord) : tx_bytes) : "memory");
+                    int64_t a0 = a_base + (int64_t)sk * ld - dk;
+                    if (dbg & 4) a0 = a_base + (int64_t)(blockIdx.x & 63) * ld;   // experiment
+                    for (int bs = 0; bs < ((dbg & 8) ? 0 : n_act_bands); ++bs, a0 += a_band) {
+                        const int32_t row0 = (int32_t)(a0 >> 4);       // tensor row (floor)
                         asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                            ::"r"(smem_u32(st + kBoxArea)), "l"(recs + e + k),
-                            "r"((uint32_t)sizeof(WinRecord)), "r"(smem_u32(&smem_full[stage]))
+                            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                            "[%0], [%1, {%2, %3}], [%4];" ::"r"(st + bs * box_stride),
+                            "l"(&tmap), "r"(0), "r"(row0), "r"(bar)
                             : "memory");
                     }
-                    if (++stage == kSmemStages) { stage = 0; phase ^= 1; }
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                        ::"r"(st + kBoxArea), "l"(rp + e + k),
+                        "r"((uint32_t)sizeof(WinRecord)), "r"(bar)
+                        : "memory");
                 }
+                if (++stage == kSmemStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 8) {
@@ -279,44 +359,61 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsFill));
         const int q = warp - 8;
         if (q_active(q)) {
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
             const int rb = (q % qpb) * 32 + lane;           // the lane's row inside its box
-            const int box_off = (q / qpb) * box_stride;
-            int ss = 0, ts = 0;
-            uint32_t sphase = 0, tphase = 0;
-            for (int64_t e = e0; e < e1; ++e) {
-                mbar_wait(&smem_full[ss], sphase);
-                const unsigned char *st = stages + (size_t)ss * kStageBytes;
-                const WinRecord *rec = reinterpret_cast<const WinRecord *>(st + kBoxArea);
-                // 16-byte chunk at which lane 0's row starts inside its first tensor row
-                const int joff = (int)(((uint32_t)(-(rec->dbase + H))) & 15u) >> 1;
-                uint32_t v[C::kCols];
+            // offset of the lane's tensor rows 0..2 inside a stage, swizzle key folded in
+            uint32_t row_off[3];
 #pragma unroll
-                for (int ch = 0; ch < C::kChunks; ++ch) {
-                    const int lc = ch + joff;
-                    const int row = rb + (lc >> 3);
-                    const int chunk = (lc & 7) ^ (row & 7);
-                    const uint4 x = *reinterpret_cast<const uint4 *>(st + box_off + row * 128 +
-                                                                     chunk * 16);
-                    v[4 * ch] = x.x; v[4 * ch + 1] = x.y; v[4 * ch + 2] = x.z; v[4 * ch + 3] = x.w;
-                }
-                // the record (weights, shifts) travels with the TMEM stage
+            for (int j = 0; j < 3; ++j)
+                row_off[j] = (uint32_t)((q / qpb) * box_stride + (rb + j) * 128 + (((rb + j) & 7) << 4));
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            uint32_t st = sm_stages, sfull = sm_full;            // smem_empty = sfull + 8 S
+            uint32_t tfull = tm_full + 8 * q;                    // tmem_empty = tfull + 32 TS
+            uint32_t slot = sm_slots + q * kRecSlot + 8 * lane, tcol = trow;
+            int ss = 0, ts = 0;
+            uint32_t sphase = 0, tphase = 1;
+            for (int e = n_rec; e > 0; --e) {
+                mbar_wait_a(sfull, sphase);
+                // weights (lanes 0..7) and shifts (lane 8) of the record; the shifts are
+                // turned into TMEM column offsets 2 * rel (0 for an empty slot)
                 uint64_t rec_word = 0;
-                if (lane < 10) rec_word = reinterpret_cast<const uint64_t *>(rec)[lane];
-                mbar_wait(&tmem_empty[ts * 4 + q], tphase ^ 1);
+                if (lane < 9) rec_word = lds64(st + kBoxArea + 8 * lane);
+                // 16-byte chunk at which lane 0's row starts inside its first tensor row
+                const int dbase = (int)lds32(st + kBoxArea + 76);
+                const int joff = (int)(((uint32_t)(-(dbase + H))) & 15u) >> 1;
+                if (lane == 8) {
+                    uint32_t lo = (uint32_t)rec_word, hi = (uint32_t)(rec_word >> 32);
+                    lo &= ~__vcmpeq4(lo, 0xffffffffu);
+                    hi &= ~__vcmpeq4(hi, 0xffffffffu);
+                    rec_word = ((uint64_t)(hi + hi) << 32) | (uint64_t)(lo + lo);
+                }
+                const uint32_t p[3] = {st + row_off[0], st + row_off[1], st + row_off[2]};
+                mbar_wait_a(tfull + 32 * TS, tphase);
                 tc_fence_after();
-                tmem_store_row<C::kCols>(trow + (uint32_t)(ts * C::kCols), v);
-                if (lane < 10)
-                    reinterpret_cast<uint64_t *>(rec_slots + (ts * 4 + q) * kRecSlot)[lane] = rec_word;
+                if (!(dbg & 2)) switch (joff) {                    // warp-uniform
+                    case 0: fill_row<H, 0>(p, tcol); break;
+                    case 1: fill_row<H, 1>(p, tcol); break;
+                    case 2: fill_row<H, 2>(p, tcol); break;
+                    case 3: fill_row<H, 3>(p, tcol); break;
+                    case 4: fill_row<H, 4>(p, tcol); break;
+                    case 5: fill_row<H, 5>(p, tcol); break;
+                    case 6: fill_row<H, 6>(p, tcol); break;
+                    default: fill_row<H, 7>(p, tcol); break;
+                }
+                if (lane < 9) sts64(slot, rec_word);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&smem_empty[ss]);
-                    mbar_arrive(&tmem_full[ts * 4 + q]);
+                    mbar_arrive_a(sfull + 8 * kSmemStages);
+                    mbar_arrive_a(tfull);
                 }
-                if (++ss == kSmemStages) { ss = 0; sphase ^= 1; }
-                if (++ts == TS) { ts = 0; tphase ^= 1; }
+                st += kStageBytes; sfull += 8;
+                if (++ss == kSmemStages) { ss = 0; sphase ^= 1; st = sm_stages; sfull = sm_full; }
+                tfull += 32; slot += 4 * kRecSlot; tcol += C::kCols;
+                if (++ts == TS) {
+                    ts = 0; tphase ^= 1;
+                    tfull = tm_full + 8 * q; slot = sm_slots + q * kRecSlot + 8 * lane; tcol = trow;
+                }
             }
         }
     } else {
@@ -324,40 +421,66 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
         const int q = warp & 3, grp = warp >> 2;
         if (q_active(q)) {
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
             double acc[4][kLaneT];
 #pragma unroll
             for (int s = 0; s < 4; ++s)
 #pragma unroll
                 for (int k = 0; k < kLaneT; ++k) acc[s][k] = 0.0;
+            // Software pipeline over the 4 receivers of this warp's group: the two x16
+            // loads of receiver s + 1 are in flight while the 16 DFMAs of receiver s run;
+            // tcgen05.wait::ld always has exactly one receiver's loads to wait for.  Empty
+            // slots have w = 0 and read the window at shift 0 (finite energies, a numerical
+            // no-op), which keeps the pipeline branch-free.
+            const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * H;
+            const uint32_t slot0 = sm_slots + q * kRecSlot + 32 * grp;   // this group's weights
+            uint32_t col = col0, slot = slot0;
+            uint32_t tfull = tm_full + 8 * q, tempty = tm_empty + 8 * q;
             int ts = 0;
             uint32_t tphase = 0;
-            for (int64_t e = e0; e < e1; ++e) {
-                mbar_wait(&tmem_full[ts * 4 + q], tphase);
+            double w[4];
+            uint32_t adr[4];
+            uint32_t x[32];
+#define SPB_READ_META()                                                                  \
+            do {                                                                         \
+                lds_f64x2(w[0], w[1], slot);                                             \
+                lds_f64x2(w[2], w[3], slot + 16);                                        \
+                const uint32_t off4 = lds32(slot + 64 - 28 * grp);                       \
+                adr[0] = col - (off4 & 0xffu);                                           \
+                adr[1] = col - ((off4 >> 8) & 0xffu);                                    \
+                adr[2] = col - ((off4 >> 16) & 0xffu);                                   \
+                adr[3] = col - (off4 >> 24);                                             \
+            } while (0)
+#define SPB_FMA16(S_, X_, W_)                                                            \
+            _Pragma("unroll") for (int k = 0; k < kLaneT; ++k)                           \
+                acc[S_][k] = fma(W_, __hiloint2double((int)X_[2 * k + 1], (int)X_[2 * k]), \
+                                 acc[S_][k])
+            // Per receiver: two x16 loads, one wait, 16 DFMAs.  No software pipeline inside
+            // the warp (it would cost 32 more registers, which the fill warps need more):
+            // the two consumer warps of a scheduler overlap each other's TMEM latency.
+            for (int n = n_rec; n > 0; --n) {
+                mbar_wait_a(tfull, tphase);
                 tc_fence_after();
-                const unsigned char *slot = rec_slots + (ts * 4 + q) * kRecSlot;
-                const double2 w01 = *reinterpret_cast<const double2 *>(slot + 32 * grp);
-                const double2 w23 = *reinterpret_cast<const double2 *>(slot + 32 * grp + 16);
-                const uint32_t rel4 = *reinterpret_cast<const uint32_t *>(slot + 64 + 4 * grp);
-                const double w[4] = {w01.x, w01.y, w23.x, w23.y};
-                const uint32_t tstage = trow + (uint32_t)(ts * C::kCols + 2 * H);
+                SPB_READ_META();
+                if (!(dbg & 1)) {
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const uint32_t r = (rel4 >> (8 * s)) & 0xffu;
-                    if (r != 255u) {                                   // warp-uniform
-                        uint32_t x[32];
-                        tmem_ld16x2(x, tstage - 2 * r);
-#pragma unroll
-                        for (int k = 0; k < kLaneT; ++k)
-                            acc[s][k] = fma(w[s], __hiloint2double((int)x[2 * k + 1], (int)x[2 * k]),
-                                            acc[s][k]);
+                    for (int s2 = 0; s2 < 4; ++s2) {
+                        tmem_ld16(x, adr[s2]);
+                        tmem_ld16(x + 16, adr[s2] + 16);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        SPB_FMA16(s2, x, w[s2]);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[ts * 4 + q]);
-                if (++ts == TS) { ts = 0; tphase ^= 1; }
+                if (lane == 0) mbar_arrive_a(tempty);
+                tfull += 32; tempty += 32; slot += 4 * kRecSlot; col += C::kCols;
+                if (++ts == TS) {
+                    ts = 0; tphase ^= 1;
+                    tfull = tm_full + 8 * q; tempty = tm_empty + 8 * q; slot = slot0; col = col0;
+                }
             }
+#undef SPB_READ_META
+#undef SPB_FMA16
             // ---- epilogue: 16 consecutive bins per receiver row ----
             const int64_t b = q_band(q);
             const int64_t t0 = q_t0(q) + (int64_t)lane * kLaneT;
@@ -440,11 +563,13 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
                         (2 * kSmemStages + 8 * C::kTmemStages) * sizeof(uint64_t) + 16;
     SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
+    const char *dbg_env = getenv("SPB_TMEM_DBG");          // timing experiments only
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     dim3 grid((unsigned)n_tiles, (unsigned)(n_bgroups * n_tchunks));
     k_gather_tmem<H><<<grid, kThreads, smem, st>>>(tmap, g, ent_ptr, recs, cta_order, n_patches,
                                                    n_alloc, n_blocks, n_dirs, b_lo, b_hi, jb_lo,
                                                    n_jb, n_classes, t_pad, ld, pad, qpb,
-                                                   n_tchunks);
+                                                   n_tchunks, dbg);
     return check_launch("k_gather_tmem");
 }
 

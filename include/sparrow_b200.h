@@ -151,7 +151,10 @@ int spb_exchange_gather_window(const void *e_prev, void *g, const int64_t *ent_p
  * feeds the FMAs from a datapath three times wider than shared memory.
  * Replaces the inner loops of _energy_exchange (RadiosityFast.py:1121-1144).  e_prev
  * must be the base of the whole (n_bands * n_alloc * n_dirs, ld) histogram, 16-byte
- * aligned. */
+ * aligned.  The pipeline hands records over in batches: every tile's record list must be
+ * padded to a multiple of spb_tmem_batch() with null records (w = 0, rel = 255, src = 0,
+ * dbase = 0). */
+int spb_tmem_batch(void);
 int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr,
                              const void *recs, const int32_t *cta_order,
                              int64_t n_patches, int64_t n_alloc, int64_t n_classes,

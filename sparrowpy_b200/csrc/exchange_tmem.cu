@@ -46,9 +46,8 @@ namespace tmg {
 constexpr int kR = 8;                          // receivers per tile
 constexpr int kLaneT = 16;                     // consecutive time bins per TMEM lane
 constexpr int kQuarterT = 32 * kLaneT;         // 512 bins per lane quarter
-constexpr int kSmemStages = 8;
-constexpr int kBoxArea = 20480;                // bytes reserved for the staged boxes
-constexpr int kStageBytes = 21504;             // box area + record, multiple of 1024
+constexpr int kBoxArea = 20480;                // bytes reserved for the staged boxes of a record
+constexpr int kBatch = 2;                      // records per pipeline hand-over
 constexpr int kRecSlot = 96;                   // bytes per (TMEM stage, quarter) record copy
 constexpr int kThreads = 512;   // 8 consumer + 4 fill + 1 producer (+ 3 idle) warps; 512 x 128 regs
                                 // at launch = the whole file, so setmaxnreg only re-deals it
@@ -241,7 +240,7 @@ __device__ __forceinline__ void fill_row(const uint32_t (&p)[3], uint32_t taddr)
     tmem_store_row<C::kCols>(taddr, v);
 }
 
-template <int H>
+template <int H, int B>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
               const int64_t *__restrict__ ent_ptr, const WinRecord *__restrict__ recs,
@@ -249,18 +248,26 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
               int64_t n_blocks, int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t jb_lo,
               int64_t n_jb, int64_t n_classes, int64_t t_pad, int64_t ld, int64_t pad, int qpb,
               int n_tchunks, int dbg) {
+    // Every hand-over of the pipeline (producer -> fill -> consumers) moves a BATCH of B
+    // records: the barrier waits, fences and arrivals are a serial chain of a few hundred
+    // cycles per hand-over in every role, and per single record that chain, not any
+    // bandwidth, bounded the kernel (measured: 480 clk per record with no data moved at all).
     using C = Cfg<H>;
-    constexpr int TS = C::kTmemStages;
+    constexpr int S = 8 / B;                           // shared-memory stages (of B records)
+    constexpr int TS = 512 / (B * C::kCols);           // TMEM stages (of B rows per lane)
+    constexpr int kStage = B * kBoxArea + 1024;        // boxes + the B records
+    constexpr int kSlot = B * kRecSlot;                // per (TMEM stage, quarter)
+    static_assert(TS >= 2 && S >= 2, "double buffering");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: kSmemStages x kStageBytes | rec slots [TS][4][kRecSlot] | barriers | tmem slot
+    // layout: S x kStage | rec slots [TS][4][B][kRecSlot] | barriers | tmem slot
     const uint32_t sm_stages = smem_u32(smem_raw);
-    const uint32_t sm_slots = sm_stages + kSmemStages * kStageBytes;
-    const uint32_t sm_full = sm_slots + TS * 4 * kRecSlot;           // smem_full[kSmemStages]
-    const uint32_t sm_empty = sm_full + 8 * kSmemStages;              // smem_empty[kSmemStages]
-    const uint32_t tm_full = sm_empty + 8 * kSmemStages;              // tmem_full[TS][4]
+    const uint32_t sm_slots = sm_stages + S * kStage;
+    const uint32_t sm_full = sm_slots + TS * 4 * kSlot;               // smem_full[S]
+    const uint32_t sm_empty = sm_full + 8 * S;                        // smem_empty[S]
+    const uint32_t tm_full = sm_empty + 8 * S;                        // tmem_full[TS][4]
     const uint32_t tm_empty = tm_full + 8 * TS * 4;                   // tmem_empty[TS][4]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(
-        smem_raw + kSmemStages * kStageBytes + TS * 4 * kRecSlot + 16 * kSmemStages + 64 * TS);
+        smem_raw + S * kStage + TS * 4 * kSlot + 16 * S + 64 * TS);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -272,8 +279,8 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
     const int64_t jb = jb_lo + (loc - c * n_jb);
     const int64_t tile = c * n_blocks + jb;
     const int64_t e0 = ent_ptr[tile];
-    const int n_rec = (int)(ent_ptr[tile + 1] - e0);
-    if (n_rec == 0) return;                            // no pairs: rows are never read
+    const int n_bat = (int)((ent_ptr[tile + 1] - e0) / B);   // record lists are padded to B
+    if (n_bat == 0) return;                            // no pairs: rows are never read
     const int bands_per_cta = 4 / qpb;
     const int64_t bg = blockIdx.y / n_tchunks;
     const int64_t tc = blockIdx.y - bg * n_tchunks;
@@ -291,7 +298,7 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
     const int box_stride = (box_rows * 128 + 1023) & ~1023;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSmemStages; ++s) {
+        for (int s = 0; s < S; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_full + 8 * s), "r"(1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_empty + 8 * s),
                          "r"(n_act_q));
@@ -315,43 +322,49 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
     if (warp >= 12) {
         // ---------------- producer warp (one working lane) ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
-        const uint32_t tx_bytes = (uint32_t)(n_act_bands * box_rows * 128 + sizeof(WinRecord));
+        const uint32_t tx_bytes =
+            (uint32_t)(B * (n_act_bands * box_rows * 128 + (int)sizeof(WinRecord)));
         // first double of lane 0's row = a_base + band slot * a_band + src * ld - dbase
         const int64_t a_band = n_alloc * n_dirs * ld;
         const int64_t a_base = band0 * a_band + pad + t_base - H;
         const WinRecord *rp = recs + e0;
+        const int n_rec = n_bat * B;
         int stage = 0;
         uint32_t phase = 0;
         for (int e = 0; e < (warp == 12 ? n_rec : 0); e += 32) {    // warps 13..15 idle
             int32_t s = 0, db = 0;
             if (e + lane < n_rec) { s = rp[e + lane].src; db = rp[e + lane].dbase; }
             const int cnt = min(32, n_rec - e);
-            for (int k = 0; k < cnt; ++k) {
-                const int32_t sk = __shfl_sync(0xffffffffu, s, k);
-                const int32_t dk = __shfl_sync(0xffffffffu, db, k);
+            for (int k = 0; k < cnt; k += B) {
                 if (lane == 0) {
                     mbar_wait_a(sm_empty + 8 * stage, phase ^ 1);
-                    const uint32_t bar = sm_full + 8u * stage;
-                    const uint32_t st = sm_stages + (uint32_t)stage * kStageBytes;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                                 "r"((dbg & 8) ? (uint32_t)sizeof(WinRecord) : tx_bytes) : "memory");
-                    int64_t a0 = a_base + (int64_t)sk * ld - dk;
-                    if (dbg & 4) a0 = a_base + (int64_t)(blockIdx.x & 63) * ld;   // experiment
-                    for (int bs = 0; bs < ((dbg & 8) ? 0 : n_act_bands); ++bs, a0 += a_band) {
-                        const int32_t row0 = (int32_t)(a0 >> 4);       // tensor row (floor)
-                        asm volatile(
-                            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-                            "[%0], [%1, {%2, %3}], [%4];" ::"r"(st + bs * box_stride),
-                            "l"(&tmap), "r"(0), "r"(row0), "r"(bar)
-                            : "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                                     sm_full + 8u * stage), "r"(tx_bytes) : "memory");
+                }
+#pragma unroll
+                for (int r = 0; r < B; ++r) {
+                    const int32_t sk = __shfl_sync(0xffffffffu, s, k + r);
+                    const int32_t dk = __shfl_sync(0xffffffffu, db, k + r);
+                    if (lane == 0) {
+                        const uint32_t st = sm_stages + (uint32_t)stage * kStage + r * kBoxArea;
+                        int64_t a0 = a_base + (int64_t)sk * ld - dk;
+                        for (int bs = 0; bs < ((dbg & 8) ? 0 : n_act_bands); ++bs, a0 += a_band) {
+                            const int32_t row0 = (int32_t)(a0 >> 4);       // tensor row (floor)
+                            asm volatile(
+                                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                                "[%0], [%1, {%2, %3}], [%4];" ::"r"(st + bs * box_stride),
+                                "l"(&tmap), "r"(0), "r"(row0), "r"(sm_full + 8u * stage)
+                                : "memory");
+                        }
                     }
+                }
+                if (lane == 0)
                     asm volatile(
                         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                        ::"r"(st + kBoxArea), "l"(rp + e + k),
-                        "r"((uint32_t)sizeof(WinRecord)), "r"(bar)
+                        ::"r"(sm_stages + (uint32_t)stage * kStage + B * kBoxArea), "l"(rp + e + k),
+                        "r"((uint32_t)(B * sizeof(WinRecord))), "r"(sm_full + 8u * stage)
                         : "memory");
-                }
-                if (++stage == kSmemStages) { stage = 0; phase ^= 1; }
+                if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 8) {
@@ -360,7 +373,7 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
         const int q = warp - 8;
         if (q_active(q)) {
             const int rb = (q % qpb) * 32 + lane;           // the lane's row inside its box
-            // offset of the lane's tensor rows 0..2 inside a stage, swizzle key folded in
+            // offset of the lane's tensor rows 0..2 inside a box, swizzle key folded in
             uint32_t row_off[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j)
@@ -368,51 +381,57 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
             uint32_t st = sm_stages, sfull = sm_full;            // smem_empty = sfull + 8 S
             uint32_t tfull = tm_full + 8 * q;                    // tmem_empty = tfull + 32 TS
-            uint32_t slot = sm_slots + q * kRecSlot + 8 * lane, tcol = trow;
+            uint32_t slot = sm_slots + q * kSlot + 8 * lane, tcol = trow;
             int ss = 0, ts = 0;
             uint32_t sphase = 0, tphase = 1;
-            for (int e = n_rec; e > 0; --e) {
+            for (int e = n_bat; e > 0; --e) {
                 mbar_wait_a(sfull, sphase);
-                // weights (lanes 0..7) and shifts (lane 8) of the record; the shifts are
-                // turned into TMEM column offsets 2 * rel (0 for an empty slot)
-                uint64_t rec_word = 0;
-                if (lane < 9) rec_word = lds64(st + kBoxArea + 8 * lane);
-                // 16-byte chunk at which lane 0's row starts inside its first tensor row
-                const int dbase = (int)lds32(st + kBoxArea + 76);
-                const int joff = (int)(((uint32_t)(-(dbase + H))) & 15u) >> 1;
-                if (lane == 8) {
-                    uint32_t lo = (uint32_t)rec_word, hi = (uint32_t)(rec_word >> 32);
-                    lo &= ~__vcmpeq4(lo, 0xffffffffu);
-                    hi &= ~__vcmpeq4(hi, 0xffffffffu);
-                    rec_word = ((uint64_t)(hi + hi) << 32) | (uint64_t)(lo + lo);
-                }
-                const uint32_t p[3] = {st + row_off[0], st + row_off[1], st + row_off[2]};
                 mbar_wait_a(tfull + 32 * TS, tphase);
                 tc_fence_after();
-                if (!(dbg & 2)) switch (joff) {                    // warp-uniform
-                    case 0: fill_row<H, 0>(p, tcol); break;
-                    case 1: fill_row<H, 1>(p, tcol); break;
-                    case 2: fill_row<H, 2>(p, tcol); break;
-                    case 3: fill_row<H, 3>(p, tcol); break;
-                    case 4: fill_row<H, 4>(p, tcol); break;
-                    case 5: fill_row<H, 5>(p, tcol); break;
-                    case 6: fill_row<H, 6>(p, tcol); break;
-                    default: fill_row<H, 7>(p, tcol); break;
+#pragma unroll
+                for (int r = 0; r < B; ++r) {
+                    const uint32_t rec = st + B * kBoxArea + r * (int)sizeof(WinRecord);
+                    // weights (lanes 0..7) and shifts (lane 8) of the record; the shifts are
+                    // turned into TMEM column offsets 2 * rel (0 for an empty slot)
+                    uint64_t rec_word = 0;
+                    if (lane < 9) rec_word = lds64(rec + 8 * lane);
+                    // 16-byte chunk at which lane 0's row starts inside its first tensor row
+                    const int dbase = (int)lds32(rec + 76);
+                    const int joff = (int)(((uint32_t)(-(dbase + H))) & 15u) >> 1;
+                    if (lane == 8) {
+                        uint32_t lo = (uint32_t)rec_word, hi = (uint32_t)(rec_word >> 32);
+                        lo &= ~__vcmpeq4(lo, 0xffffffffu);
+                        hi &= ~__vcmpeq4(hi, 0xffffffffu);
+                        rec_word = ((uint64_t)(hi + hi) << 32) | (uint64_t)(lo + lo);
+                    }
+                    const uint32_t bx = st + r * kBoxArea;
+                    const uint32_t p[3] = {bx + row_off[0], bx + row_off[1], bx + row_off[2]};
+                    const uint32_t tc0 = tcol + r * C::kCols;
+                    if (!(dbg & 2)) switch (joff) {                // warp-uniform
+                        case 0: fill_row<H, 0>(p, tc0); break;
+                        case 1: fill_row<H, 1>(p, tc0); break;
+                        case 2: fill_row<H, 2>(p, tc0); break;
+                        case 3: fill_row<H, 3>(p, tc0); break;
+                        case 4: fill_row<H, 4>(p, tc0); break;
+                        case 5: fill_row<H, 5>(p, tc0); break;
+                        case 6: fill_row<H, 6>(p, tc0); break;
+                        default: fill_row<H, 7>(p, tc0); break;
+                    }
+                    if (lane < 9) sts64(slot + r * kRecSlot, rec_word);
                 }
-                if (lane < 9) sts64(slot, rec_word);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive_a(sfull + 8 * kSmemStages);
+                    mbar_arrive_a(sfull + 8 * S);
                     mbar_arrive_a(tfull);
                 }
-                st += kStageBytes; sfull += 8;
-                if (++ss == kSmemStages) { ss = 0; sphase ^= 1; st = sm_stages; sfull = sm_full; }
-                tfull += 32; slot += 4 * kRecSlot; tcol += C::kCols;
+                st += kStage; sfull += 8;
+                if (++ss == S) { ss = 0; sphase ^= 1; st = sm_stages; sfull = sm_full; }
+                tfull += 32; slot += 4 * kSlot; tcol += B * C::kCols;
                 if (++ts == TS) {
                     ts = 0; tphase ^= 1;
-                    tfull = tm_full + 8 * q; slot = sm_slots + q * kRecSlot + 8 * lane; tcol = trow;
+                    tfull = tm_full + 8 * q; slot = sm_slots + q * kSlot + 8 * lane; tcol = trow;
                 }
             }
         }
@@ -426,61 +445,50 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
             for (int s = 0; s < 4; ++s)
 #pragma unroll
                 for (int k = 0; k < kLaneT; ++k) acc[s][k] = 0.0;
-            // Software pipeline over the 4 receivers of this warp's group: the two x16
-            // loads of receiver s + 1 are in flight while the 16 DFMAs of receiver s run;
-            // tcgen05.wait::ld always has exactly one receiver's loads to wait for.  Empty
-            // slots have w = 0 and read the window at shift 0 (finite energies, a numerical
-            // no-op), which keeps the pipeline branch-free.
             const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * H;
-            const uint32_t slot0 = sm_slots + q * kRecSlot + 32 * grp;   // this group's weights
+            const uint32_t slot0 = sm_slots + q * kSlot + 32 * grp;   // this group's weights
             uint32_t col = col0, slot = slot0;
-            uint32_t tfull = tm_full + 8 * q, tempty = tm_empty + 8 * q;
+            uint32_t tfull = tm_full + 8 * q;                          // tmem_empty = + 32 TS
             int ts = 0;
             uint32_t tphase = 0;
-            double w[4];
-            uint32_t adr[4];
-            uint32_t x[32];
-#define SPB_READ_META()                                                                  \
-            do {                                                                         \
-                lds_f64x2(w[0], w[1], slot);                                             \
-                lds_f64x2(w[2], w[3], slot + 16);                                        \
-                const uint32_t off4 = lds32(slot + 64 - 28 * grp);                       \
-                adr[0] = col - (off4 & 0xffu);                                           \
-                adr[1] = col - ((off4 >> 8) & 0xffu);                                    \
-                adr[2] = col - ((off4 >> 16) & 0xffu);                                   \
-                adr[3] = col - (off4 >> 24);                                             \
-            } while (0)
-#define SPB_FMA16(S_, X_, W_)                                                            \
-            _Pragma("unroll") for (int k = 0; k < kLaneT; ++k)                           \
-                acc[S_][k] = fma(W_, __hiloint2double((int)X_[2 * k + 1], (int)X_[2 * k]), \
-                                 acc[S_][k])
-            // Per receiver: two x16 loads, one wait, 16 DFMAs.  No software pipeline inside
-            // the warp (it would cost 32 more registers, which the fill warps need more):
-            // the two consumer warps of a scheduler overlap each other's TMEM latency.
-            for (int n = n_rec; n > 0; --n) {
+            // Per receiver: two x16 loads, one wait, 16 DFMAs; the two consumer warps of a
+            // scheduler overlap each other's TMEM latency.  Empty slots have w = 0 and read
+            // the window at shift 0 (finite energies, a numerical no-op): no branches.
+            for (int n = n_bat; n > 0; --n) {
                 mbar_wait_a(tfull, tphase);
                 tc_fence_after();
-                SPB_READ_META();
-                if (!(dbg & 1)) {
 #pragma unroll
-                    for (int s2 = 0; s2 < 4; ++s2) {
-                        tmem_ld16(x, adr[s2]);
-                        tmem_ld16(x + 16, adr[s2] + 16);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        SPB_FMA16(s2, x, w[s2]);
+                for (int r = 0; r < B; ++r) {
+                    double w[4];
+                    lds_f64x2(w[0], w[1], slot + r * kRecSlot);
+                    lds_f64x2(w[2], w[3], slot + r * kRecSlot + 16);
+                    const uint32_t off4 = lds32(slot + r * kRecSlot + 64 - 28 * grp);
+                    const uint32_t cr = col + r * C::kCols;
+                    if (!(dbg & 1)) {
+#pragma unroll
+                        for (int s2 = 0; s2 < 4; ++s2) {
+                            uint32_t x[32];
+                            const uint32_t adr = cr - ((off4 >> (8 * s2)) & 0xffu);
+                            tmem_ld16(x, adr);
+                            tmem_ld16(x + 16, adr + 16);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int k = 0; k < kLaneT; ++k)
+                                acc[s2][k] = fma(w[s2],
+                                                 __hiloint2double((int)x[2 * k + 1], (int)x[2 * k]),
+                                                 acc[s2][k]);
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_a(tempty);
-                tfull += 32; tempty += 32; slot += 4 * kRecSlot; col += C::kCols;
+                if (lane == 0) mbar_arrive_a(tfull + 32 * TS);
+                tfull += 32; slot += 4 * kSlot; col += B * C::kCols;
                 if (++ts == TS) {
                     ts = 0; tphase ^= 1;
-                    tfull = tm_full + 8 * q; tempty = tm_empty + 8 * q; slot = slot0; col = col0;
+                    tfull = tm_full + 8 * q; slot = slot0; col = col0;
                 }
             }
-#undef SPB_READ_META
-#undef SPB_FMA16
             // ---- epilogue: 16 consecutive bins per receiver row ----
             const int64_t b = q_band(q);
             const int64_t t0 = q_t0(q) + (int64_t)lane * kLaneT;
@@ -522,7 +530,7 @@ static EncodeTiled encode_fn() {
     return fn;
 }
 
-template <int H>
+template <int H, int B>
 int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRecord *recs,
            const int32_t *cta_order, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
            int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
@@ -559,14 +567,15 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled", "encode failed");
 
-    const size_t smem = (size_t)kSmemStages * kStageBytes + (size_t)C::kTmemStages * 4 * kRecSlot +
-                        (2 * kSmemStages + 8 * C::kTmemStages) * sizeof(uint64_t) + 16;
-    SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    constexpr int S = 8 / B, TS = 512 / (B * C::kCols);
+    const size_t smem = (size_t)S * (B * kBoxArea + 1024) + (size_t)TS * 4 * B * kRecSlot +
+                        (2 * S + 8 * TS) * sizeof(uint64_t) + 16;
+    SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     const char *dbg_env = getenv("SPB_TMEM_DBG");          // timing experiments only
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     dim3 grid((unsigned)n_tiles, (unsigned)(n_bgroups * n_tchunks));
-    k_gather_tmem<H><<<grid, kThreads, smem, st>>>(tmap, g, ent_ptr, recs, cta_order, n_patches,
+    k_gather_tmem<H, B><<<grid, kThreads, smem, st>>>(tmap, g, ent_ptr, recs, cta_order, n_patches,
                                                    n_alloc, n_blocks, n_dirs, b_lo, b_hi, jb_lo,
                                                    n_jb, n_classes, t_pad, ld, pad, qpb,
                                                    n_tchunks, dbg);
@@ -579,6 +588,8 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
 using namespace spb;
 
 extern "C" {
+
+int spb_tmem_batch(void) { return tmg::kBatch; }
 
 int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr,
                              const void *recs, const int32_t *cta_order, int64_t n_patches,
@@ -599,10 +610,10 @@ int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr
     const double *ep = (const double *)e_prev;
     const tmg::WinRecord *r = (const tmg::WinRecord *)recs;
     if (window == 4)
-        return tmg::launch<4>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc, n_classes,
+        return tmg::launch<4, tmg::kBatch>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc, n_classes,
                              n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
     if (window == 10)
-        return tmg::launch<10>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
+        return tmg::launch<10, tmg::kBatch>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
                               n_classes, n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad,
                               st);
     return fail(-1, "invalid argument", "window must be 4 or 10");

@@ -94,7 +94,7 @@ def gather_kind(code=None):
     return kind
 
 
-DEFAULT_GATHER = "tma"
+DEFAULT_GATHER = "tmem"
 
 
 def window_arg(tables):
@@ -187,6 +187,8 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     if gather in ("win", "tmem") and code == _lib.F64:
         win_ptr, win_recs, win_w = build_window_records(
             sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs, n_classes, code)
+        if gather == "tmem":
+            win_ptr, win_recs = pad_record_lists(win_ptr, win_recs, tmem_batch())
     else:
         ent_ptr, recs = build_tile_records(sender, receiver, ff, delay, out_dir, cls,
                                            n_patches, n_dirs, n_classes, code)
@@ -308,6 +310,30 @@ def _window_cover(delay_sorted, group, pos, n_groups, n_r, width, align=2):
         start[idx] = new
         ebase[idx] = base[gp]
     return start, ebase
+
+
+def tmem_batch():
+    """Records per pipeline hand-over of the tensor-memory gather (csrc/exchange_tmem.cu):
+    every tile's record list is padded to a multiple of it."""
+    return int(_lib.load().spb_tmem_batch())
+
+
+def pad_record_lists(ent_ptr, recs, multiple):
+    """Pad every tile's record list to a multiple of ``multiple`` with null records
+    (w = 0, rel = 255, src = 0, dbase = 0: they add nothing)."""
+    if multiple <= 1 or recs.shape[0] == 0:
+        return ent_ptr, recs
+    counts = ent_ptr[1:] - ent_ptr[:-1]
+    padded = -(-counts // multiple) * multiple
+    new_ptr = torch.zeros_like(ent_ptr)
+    new_ptr[1:] = torch.cumsum(padded, 0)
+    n_new = int(new_ptr[-1].item())
+    out = torch.zeros((n_new, recs.shape[1]), dtype=torch.uint8, device=recs.device)
+    out[:, 64:72] = 255                                     # rel of a null record
+    tile = torch.repeat_interleave(torch.arange(counts.numel(), device=recs.device), counts)
+    dst = torch.arange(recs.shape[0], device=recs.device) + (new_ptr[:-1] - ent_ptr[:-1])[tile]
+    out[dst] = recs
+    return new_ptr.contiguous(), out
 
 
 def build_window_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs,

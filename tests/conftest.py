@@ -15,13 +15,9 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu)")
 
 
-# golden scenes the GPU parity tests run on.  The last two were generated (and the oracle
-# and the host twins pinned on them) after the GPU budget of round 1 was spent: they join
-# the unattended GPU run once they have passed there (SPB_EXPERIMENTAL=1 runs them now).
+# golden scenes the GPU parity tests run on (all seven fixtures of tests/golden)
 GPU_SCENES = ["scene_cube05", "scene_c1", "scene_occluder", "scene_directional",
-              "scene_canyon01"]
-if os.environ.get("SPB_EXPERIMENTAL") == "1":
-    GPU_SCENES += ["scene_uneven", "scene_canyon015_dir"]
+              "scene_canyon01", "scene_uneven", "scene_canyon015_dir"]
 
 
 def load_golden(name):

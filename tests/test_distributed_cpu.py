@@ -219,8 +219,8 @@ def test_shard_restricted_tables_partition_the_full_tables():
                 assert torch.equal(full.dly[a0:a1], part.dly[b0:b1])
                 assert torch.equal(full.wgt[a0:a1], part.wgt[b0:b1])
         # tile records of the shard's tiles are those of the full tables
-        rec_full = (full.ent_ptr[1:] - full.ent_ptr[:-1]).view(full.n_classes, -1)
-        rec_part = (part.ent_ptr[1:] - part.ent_ptr[:-1]).view(full.n_classes, -1)
+        rec_full = (full.tile_ptr[1:] - full.tile_ptr[:-1]).view(full.n_classes, -1)
+        rec_part = (part.tile_ptr[1:] - part.tile_ptr[:-1]).view(full.n_classes, -1)
         assert torch.equal(rec_part[:, lo // 8:-(-hi // 8)], rec_full[:, lo // 8:-(-hi // 8)])
         seen += int(cnt_part.sum())
     assert seen == full.src.numel()

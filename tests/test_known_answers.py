@@ -273,12 +273,7 @@ def plane_ratio_cuda(source, receiver):
     return float(np.sum(etc.time))
 
 
-UNVERIFIED_GPU = pytest.mark.skipif(
-    __import__("os").environ.get("SPB_EXPERIMENTAL") != "1",
-    reason="one-bin histograms have not run on a GPU yet (set SPB_EXPERIMENTAL=1)")
-
-
-@pytest.fixture(params=["oracle", pytest.param("cuda", marks=[pytest.mark.gpu, UNVERIFIED_GPU])])
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=[pytest.mark.gpu])])
 def plane_ratio(request, oracle):
     def ratio(source, receiver):
         image = np.array([source[0], source[1], -source[2]])

@@ -1,9 +1,6 @@
 """Band-by-band, sharded-total schedule (distributed.BandwiseExchange) on one GPU against
 the ordinary exchange, on the two-band golden scene.  The schedule's choreography is
-covered on the CPU (tests/test_distributed_cpu.py); this runs it with the CUDA kernels.
-Gated until it has run on a GPU once (set SPB_EXPERIMENTAL=1)."""
-import os
-
+covered on the CPU (tests/test_distributed_cpu.py); this runs it with the CUDA kernels."""
 import numpy as np
 import pytest
 import torch
@@ -11,9 +8,7 @@ import torch
 from conftest import load_golden
 from test_exchange_gpu import device_tables, oracle_run
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SPB_EXPERIMENTAL") != "1",
-                                 reason="set SPB_EXPERIMENTAL=1 to run unverified paths")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("band_block", [1, 2])

@@ -60,7 +60,7 @@ def decode_records(t, dtype=np.float64):
 def test_csr_and_tile_records_encode_the_same_pairs(dtype):
     sender, receiver, ff, delay, out_dir, cls, coef, n, t_len = random_pairs(1)
     t = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n, t_len,
-                                   dtype)
+                                   dtype, gather="tma")
     keep = delay < t_len
     assert t.n_directed == sender.numel() and t.src.numel() == int(keep.sum())
     assert t.max_delay == int(delay[keep].max())
@@ -86,7 +86,7 @@ def test_renumbering_and_source_tiling():
     n_int = n + 11
     rank = torch.from_numpy(gen.permutation(n_int)[:n].astype(np.int64))
     t = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n, t_len,
-                                   "f64", rank=rank, n_internal=n_int)
+                                   "f64", rank=rank, n_internal=n_int, gather="tma")
     assert (t.n_patches, t.n_user) == (n_int, n)
     keep = delay < t_len
     want = sorted((int(c), int(rank[r]), int(rank[s]) * t.n_dirs + int(o), int(dl), float(w))
@@ -221,3 +221,50 @@ def test_visible_pairs_scans_the_matrix_in_row_blocks():
     assert torch.equal(whole.long(), torch.nonzero(vis))
     for block in (1, 57, 100, 57 * 5 + 3, 57 * 57):
         assert torch.equal(bake.visible_pairs(vis, max_block_elems=block), whole)
+
+
+def decode_window_records(t):
+    """(class, receiver, src_row, delay, weight) tuples encoded in the window records
+    (csrc/exchange_tmem.cu, exchange_win.cu): {w[8] f64, rel[8] u8, src i32, dbase i32}."""
+    recs, ent = t.win_recs.numpy(), t.win_ptr.numpy()
+    n_blocks = -(-t.n_patches // 8)
+    out, n_null = [], 0
+    for tile in range(len(ent) - 1):
+        c, jb = divmod(tile, n_blocks)
+        for e in range(ent[tile], ent[tile + 1]):
+            raw = recs[e]
+            w, rel = raw[:64].view(np.float64), raw[64:72]
+            src, dbase = raw[72:].view(np.int32)
+            assert dbase % 2 == 0 and dbase >= 0
+            if np.all(rel == 255):
+                assert np.all(w == 0) and src == 0 and dbase == 0      # padding record
+                n_null += 1
+            for s in range(8):
+                if rel[s] != 255:
+                    assert rel[s] <= t.win_w and w[s] != 0
+                    out.append((c, jb * 8 + s, int(src), int(dbase) + int(rel[s]), float(w[s])))
+                else:
+                    assert w[s] == 0
+    return sorted(out), n_null
+
+
+@pytest.mark.parametrize("gather", ["win", "tmem"])
+def test_window_records_encode_the_same_pairs(gather):
+    """The window records are a lossless encoding of the pair list; the tensor-memory
+    kernel's lists are padded to its batch size with null records."""
+    sender, receiver, ff, delay, out_dir, cls, coef, n, t_len = random_pairs(3)
+    t = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n, t_len,
+                                   "f64", gather=gather)
+    assert t.recs is None and t.win_recs is not None and t.win_w in exchange.WINDOW_CHOICES
+    keep = delay < t_len
+    want = sorted((int(c), int(r), int(s) * t.n_dirs + int(o), int(dl), float(w))
+                  for c, r, s, o, dl, w in zip(cls[keep], receiver[keep], sender[keep],
+                                               out_dir[keep], delay[keep], ff[keep]))
+    got, n_null = decode_window_records(t)
+    assert got == want
+    counts = (t.win_ptr[1:] - t.win_ptr[:-1]).numpy()
+    if gather == "tmem":
+        batch = exchange.tmem_batch()
+        assert np.all(counts % batch == 0) and n_null < batch * len(counts)
+    else:
+        assert n_null == 0

@@ -123,28 +123,17 @@ int spb_exchange_gather_tiled(const void *e_prev, void *g, const int64_t *ent_pt
                               int64_t t_pad, int64_t ld, int64_t pad, int dtype,
                               void *stream);
 
-/* Stage 1, register-window variant (FP64 only; same result as spb_exchange_gather).
- * For scenes whose patches are larger than a delay bin the receivers of a tile all
- * have different delays and the tiled kernel needs one shared-memory operand per FMA;
- * here a lane owns 8 consecutive time bins and loads the window of 8 + W consecutive
- * energies of a sender row once for all R = 8 receivers of the tile.  Records (80
- * bytes, geometry from spb_window_geometry):
+/* Window records of the tensor-memory gather below (80 bytes):
  *     { double w[R]; uint8 rel[R]; int32 src; int32 dbase; }
- * one per (tile, sender row, delay window [dbase, dbase + W]), dbase even,
- * rel = delay - dbase, rel = 255 for a slot without a pair.  window = W must be one of
- * the instantiated widths (4 or 10); every rel of the table must be <= W.
- * Tile numbering, ent_ptr, j_lo and cta_order as for spb_exchange_gather_tiled. */
+ * one per (tile of R = 8 receivers, sender row, delay window [dbase, dbase + W]), dbase
+ * even, rel = delay - dbase, rel = 255 for a slot without a pair; W is one of the
+ * instantiated widths (4 or 10).  Tile numbering, ent_ptr, j_lo and cta_order as for
+ * spb_exchange_gather_tiled. */
 int spb_window_geometry(int dtype, int64_t *receivers_per_tile, int64_t *max_window,
                         int64_t *record_bytes);
-int spb_exchange_gather_window(const void *e_prev, void *g, const int64_t *ent_ptr,
-                               const void *recs, const int32_t *cta_order,
-                               int64_t n_patches, int64_t n_alloc, int64_t n_classes,
-                               int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi,
-                               int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
-                               int64_t pad, int64_t window, int dtype, void *stream);
 
-/* Stage 1, tensor-memory variant (FP64 only; same result as spb_exchange_gather, same
- * records and arguments as spb_exchange_gather_window).  The sender window of a record
+/* Stage 1, tensor-memory variant (FP64 only; same result as spb_exchange_gather, window
+ * records as described above).  The sender window of a record
  * is staged by a 2-D TMA tensor load into shared memory and from there into TENSOR
  * MEMORY with time along the TMEM columns, 16 consecutive bins (+ the delay window) per
  * TMEM lane; a receiver's delay then is a dynamic column address of tcgen05.ld, which

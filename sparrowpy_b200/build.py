@@ -21,7 +21,6 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
 SOURCES = [
     ("exchange.cu", []),
     ("exchange_tma.cu", []),
-    ("exchange_win.cu", []),
     ("exchange_tmem.cu", []),
     ("bake.cu", ["--fmad=false"]),
 ]

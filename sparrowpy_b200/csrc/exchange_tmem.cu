@@ -591,6 +591,15 @@ extern "C" {
 
 int spb_tmem_batch(void) { return tmg::kBatch; }
 
+int spb_window_geometry(int dtype, int64_t *receivers_per_tile, int64_t *max_window,
+                        int64_t *record_bytes) {
+    SPB_REQUIRE(dtype == SPB_F64, "the tensor-memory gather is FP64 only");
+    *receivers_per_tile = tmg::kR;
+    *max_window = 10;
+    *record_bytes = sizeof(tmg::WinRecord);
+    return 0;
+}
+
 int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr,
                              const void *recs, const int32_t *cta_order, int64_t n_patches,
                              int64_t n_alloc, int64_t n_classes, int64_t n_dirs,

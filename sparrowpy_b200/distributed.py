@@ -57,12 +57,15 @@ class ShardedExchange:
     """
 
     def __init__(self, tables, n_samples, device, group=None, compute=None,
-                 layout=None, need_orders=True, gather_total=True):
+                 layout=None, need_orders=True, gather_total=True, local=False):
         self.t = tables
         self.gather_total = gather_total     # False: E_total stays sharded (own rows only)
         self.group = group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # local=True: a single-device run even when a process group is initialised (the
+        # class API under torchrun must not silently turn into a collective)
+        sharded = dist.is_initialized() and not local
+        self.rank = dist.get_rank(group) if sharded else 0
+        self.world = dist.get_world_size(group) if sharded else 1
         self.n_samples = n_samples
         self.j_lo, self.j_hi, self.shard = shard_range(tables.n_patches, self.rank,
                                                        self.world)

@@ -35,7 +35,7 @@ class PairTables:
     n_records: int = 0
     rank: torch.Tensor = None      # (n_user,) int64 caller's patch id -> internal index
     n_user: int = 0                # caller's patch count (n_patches is the internal one)
-    win_ptr: torch.Tensor = None   # (C*ceil(N/R) + 1,) int64  window records (SPB_GATHER=win)
+    win_ptr: torch.Tensor = None   # (C*ceil(N/R) + 1,) int64  window records (tmem gather)
     win_recs: torch.Tensor = None  # (n_records, 80) uint8
     win_w: int = 0                 # delay window of the records (4 or 10 bins)
 
@@ -82,31 +82,19 @@ def directed_pairs(pairs, ff_pairs, areas):
 
 
 def gather_kind(code=None):
-    """Stage-1 kernel selected by ``SPB_GATHER``: ``tmem`` (window records, operands from
-    tensor memory, exchange_tmem.cu; FP64 only), ``tma`` (bucket records, operands from
-    shared memory, exchange_tma.cu), ``win`` (register-window records, exchange_win.cu;
-    FP64 only) or ``csr`` (cross-check kernel).  FP32 tables fall back to ``tma``."""
+    """Stage-1 kernel selected by ``SPB_GATHER``: ``tmem`` (default; window records, operands
+    from tensor memory, exchange_tmem.cu; FP64 only), ``tma`` (bucket records, operands from
+    shared memory, exchange_tma.cu) or ``csr`` (cross-check kernel).  FP32 tables fall back
+    to ``tma``."""
     kind = os.environ.get("SPB_GATHER", DEFAULT_GATHER)
-    if kind not in ("tmem", "tma", "win", "csr"):
-        raise ValueError(f"SPB_GATHER={kind!r}: use tmem, tma, win or csr")
-    if kind in ("win", "tmem") and code is not None and code != _lib.F64:
+    if kind not in ("tmem", "tma", "csr"):
+        raise ValueError(f"SPB_GATHER={kind!r}: use tmem, tma or csr")
+    if kind == "tmem" and code is not None and code != _lib.F64:
         kind = "tma"
     return kind
 
 
 DEFAULT_GATHER = "tmem"
-
-
-def window_arg(tables):
-    """``window`` argument of spb_exchange_gather_window: the record window, plus a
-    tuning variant selected by the environment -- +100: 4 instead of 8 time bins per
-    lane (``SPB_WIN_LANE_T=4``); +200 / +300: variants 2 and 3, row copied by one warp per
-    record and jump-table dispatch per receiver / chained per record
-    (``SPB_WIN_VARIANT=2|3``)."""
-    variant = os.environ.get("SPB_WIN_VARIANT", "1")
-    if variant in ("2", "3"):
-        return tables.win_w + 100 * int(variant)
-    return tables.win_w + (100 if os.environ.get("SPB_WIN_LANE_T", "8") == "4" else 0)
 
 
 def launch_gather(tables, prev, g, cta_order, n_alloc, b_lo, b_hi, j_lo, j_hi, t_pad, ld,
@@ -117,14 +105,9 @@ def launch_gather(tables, prev, g, cta_order, n_alloc, b_lo, b_hi, j_lo, j_hi, t
     code, st = _lib.I32(t.dtype), _lib.stream_ptr()
     kind = kind or gather_kind(t.dtype)
     if t.win_recs is not None and kind != "csr":
-        if kind == "tmem":
-            _lib.call("spb_exchange_gather_tmem", prev, g, t.win_ptr, t.win_recs, cta_order,
-                      t.n_patches, n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
-                      j_lo, j_hi, t_pad, ld, pad, t.win_w, code, st)
-        else:
-            _lib.call("spb_exchange_gather_window", prev, g, t.win_ptr, t.win_recs, cta_order,
-                      t.n_patches, n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
-                      j_lo, j_hi, t_pad, ld, pad, window_arg(t), code, st)
+        _lib.call("spb_exchange_gather_tmem", prev, g, t.win_ptr, t.win_recs, cta_order,
+                  t.n_patches, n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
+                  j_lo, j_hi, t_pad, ld, pad, t.win_w, code, st)
     elif t.recs is not None and kind != "csr":
         _lib.call("spb_exchange_gather_tiled", prev, g, t.ent_ptr, t.recs, cta_order,
                   t.n_patches, n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, j_lo,
@@ -184,11 +167,10 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     gather = gather or gather_kind(code)
     ent_ptr = recs = win_ptr = win_recs = None
     win_w = 0
-    if gather in ("win", "tmem") and code == _lib.F64:
+    if gather == "tmem" and code == _lib.F64:
         win_ptr, win_recs, win_w = build_window_records(
             sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs, n_classes, code)
-        if gather == "tmem":
-            win_ptr, win_recs = pad_record_lists(win_ptr, win_recs, tmem_batch())
+        win_ptr, win_recs = pad_record_lists(win_ptr, win_recs, tmem_batch())
     else:
         ent_ptr, recs = build_tile_records(sender, receiver, ff, delay, out_dir, cls,
                                            n_patches, n_dirs, n_classes, code)
@@ -274,8 +256,8 @@ def build_tile_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_d
 
 
 def window_geometry(code):
-    """(receivers per tile, widest delay window, record bytes) of the register-window
-    gather kernel (csrc/exchange_win.cu)."""
+    """(receivers per tile, widest delay window, record bytes) of the tensor-memory
+    gather kernel (csrc/exchange_tmem.cu)."""
     import ctypes
     lib = _lib.load()
     r, q, nbytes = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
@@ -286,7 +268,7 @@ def window_geometry(code):
     return r.value, q.value, nbytes.value
 
 
-WINDOW_CHOICES = (4, 10)     # instantiations of k_gather_win
+WINDOW_CHOICES = (4, 10)     # instantiations of k_gather_tmem
 
 
 def _window_cover(delay_sorted, group, pos, n_groups, n_r, width, align=2):
@@ -338,20 +320,19 @@ def pad_record_lists(ent_ptr, recs, multiple):
 
 def build_window_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs,
                          n_classes, code, width=None, align=None):
-    """Records of the register-window gather (csrc/exchange_win.cu).
+    """Records of the tensor-memory gather (csrc/exchange_tmem.cu).
 
     A tile is R neighbouring receivers of one class.  The directed pairs of one
     (tile, sender row) are covered greedily, in order of delay, by windows
     ``[dbase, dbase + W]`` with ``dbase`` even; each window is one record
     ``{w[R] f64, rel[R] u8 (delay - dbase, 255 = no pair), src i32, dbase i32}``.
     ``W`` is the narrowest instantiated window that costs at most 2 % more records than
-    the widest one.  ``align`` (default 2, or ``SPB_WIN_ALIGN``) = 4 makes the staged rows
-    start on 32-byte sector boundaries (profiles/r01_k_gather_win_c4_f64.txt: rows that
-    start in mid-sector cost twice the L2 traffic).  Pure index bookkeeping (sort /
-    cumsum / scatter).  Returns ``(ent_ptr, recs, W)``.
+    the widest one.  ``align`` = 2 (default) keeps ``dbase`` even -- the kernel stages rows in
+    16-byte chunks; 4 is accepted for experiments.  Pure index bookkeeping (sort / cumsum /
+    scatter).  Returns ``(ent_ptr, recs, W)``.
     """
     if align is None:
-        align = int(os.environ.get("SPB_WIN_ALIGN", "2"))
+        align = 2
     if align not in (2, 4):
         raise ValueError("window alignment must be 2 or 4 bins")
     n_r, max_w, rec_bytes = window_geometry(code)
@@ -488,10 +469,10 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
 
 def _energy_exchange_orders(tables, e0, delay0, n_samples, max_order):
     """One source through the per-order driver (gather + mix launched from Python) --
-    the path of the register-window gather, which ``spb_energy_exchange`` does not
-    know about."""
+    the path of the tensor-memory gather (``spb_energy_exchange`` drives the tiled and CSR
+    kernels).  Single device, whatever process group may be initialised."""
     from .distributed import ShardedExchange
-    sx = ShardedExchange(tables, n_samples, e0.device, need_orders=max_order >= 1)
+    sx = ShardedExchange(tables, n_samples, e0.device, need_orders=max_order >= 1, local=True)
     sx.init(e0, delay0)
     return sx.run(max(0, int(max_order)))
 
@@ -503,7 +484,7 @@ def _energy_exchange_batch(tables, e0, delay0, n_samples, max_order):
     from .distributed import ShardedExchange
     n_src = e0.shape[0]
     sx = ShardedExchange(tables.tiled(n_src), n_samples, e0.device,
-                         need_orders=max_order >= 1)
+                         need_orders=max_order >= 1, local=True)
     sx.init(e0, delay0)
     hist = sx.run(max(0, int(max_order)))
     hist.n_sources = n_src

@@ -82,12 +82,12 @@ def test_argument_errors_are_reported_not_executed(lib_path):
         "multiple of the receiver tile": gather("spb_exchange_gather_tiled", null, j=(4, 8, 8)),
         "layout": gather("spb_exchange_gather_tiled", null, t_pad=250, ld=314),
         "pad": gather("spb_exchange_gather_tiled", null, ld=288, pad=32),
-        "window must be": gather("spb_exchange_gather_window", null, I64(7)),
+        "window must be": gather("spb_exchange_gather_tmem", null, I64(7)),
     }
     for text, rc in cases.items():
         assert rc < 0, text
     # the message names the violated condition
-    rc = gather("spb_exchange_gather_window", null, I64(7))
+    rc = gather("spb_exchange_gather_tmem", null, I64(7))
     assert rc < 0 and b"window must be 4 or 10" in lib.spb_last_error()
     rc = gather("spb_exchange_gather_tiled", null, j=(0, 9, 8))
     assert rc < 0 and b"receiver range" in lib.spb_last_error()
@@ -100,7 +100,7 @@ def test_geometry_queries_need_no_gpu(lib_path):
     assert exchange.tile_geometry(_lib.F32)[2] == 48
     assert exchange.window_geometry(_lib.F64) == (8, 10, 80)
     with pytest.raises(_lib.SparrowB200Error):
-        exchange.window_geometry(_lib.F32)          # the register-window kernel is FP64 only
+        exchange.window_geometry(_lib.F32)          # the tensor-memory kernel is FP64 only
     lib = _raw(lib_path)
     t_pad, pad = I64(0), I64(0)
     assert lib.spb_exchange_layout(I64(0), I64(0), INT(0), ctypes.byref(t_pad),

@@ -248,8 +248,7 @@ def decode_window_records(t):
     return sorted(out), n_null
 
 
-@pytest.mark.parametrize("gather", ["win", "tmem"])
-def test_window_records_encode_the_same_pairs(gather):
+def test_window_records_encode_the_same_pairs(gather="tmem"):
     """The window records are a lossless encoding of the pair list; the tensor-memory
     kernel's lists are padded to its batch size with null records."""
     sender, receiver, ff, delay, out_dir, cls, coef, n, t_len = random_pairs(3)
@@ -263,8 +262,5 @@ def test_window_records_encode_the_same_pairs(gather):
     got, n_null = decode_window_records(t)
     assert got == want
     counts = (t.win_ptr[1:] - t.win_ptr[:-1]).numpy()
-    if gather == "tmem":
-        batch = exchange.tmem_batch()
-        assert np.all(counts % batch == 0) and n_null < batch * len(counts)
-    else:
-        assert n_null == 0
+    batch = exchange.tmem_batch()
+    assert np.all(counts % batch == 0) and n_null < batch * len(counts)

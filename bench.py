@@ -251,6 +251,51 @@ def time_bake(rad, n_pairs):
     }
 
 
+def workload_config(cfg, name, n_patches, n_pairs, n_dir, n_band, dtype):
+    """The `config` object of the JSON line: the workload only, identical in both arms
+    (kernel / table / parallelism details go under `run`)."""
+    esize = 8 if dtype == "f64" else 4
+    hist_bytes = n_patches * n_dir * n_band * cfg["n_samples"] * esize
+    return {"workload": cfg["desc"], "name": name, "n_patches": int(n_patches),
+            "visible_pairs": int(n_pairs), "n_directions": int(n_dir), "n_bands": int(n_band),
+            "n_samples": int(cfg["n_samples"]), "reflection_orders": int(cfg["orders"]),
+            "exchanges_per_etc": 2.0 * n_pairs * cfg["n_samples"] * cfg["orders"],
+            "l2": ("inputs larger than L2 (one energy histogram = "
+                   f"{hist_bytes / 1e6:.0f} MB, 3 of them + G are streamed per order)"
+                   if hist_bytes > 126e6 * 2 else
+                   "working set fits L2 (small config, no flush)")}
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def measure_fma_peak(code, dev, reps=5):
+    """FMA-pipe peak of this GPU in the kernel's arithmetic type, measured live with the
+    register-only probe kernel of the library (csrc/peak.cu): best of `reps` launches."""
+    import ctypes
+    import torch
+    from sparrowpy_b200 import _lib
+    scratch = torch.zeros(16, dtype=torch.float64, device=dev)
+    flops = ctypes.c_double(0.0)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    best = float("inf")
+    for _ in range(reps + 1):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.call("spb_fma_peak", _lib.I32(code), 40000 if code == _lib.F64 else 80000,
+                  sms * 8, scratch, ctypes.byref(flops), _lib.stream_ptr())
+        ev1.record()
+        torch.cuda.synchronize()
+        best = min(best, ev0.elapsed_time(ev1))
+    return {"tflops": flops.value / (best * 1e-3) / 1e12, "ms": best,
+            "how": f"measured live: spb_fma_peak ({'f64' if code == _lib.F64 else 'f32'} FMA "
+                   f"chains, {sms * 8} x 256 threads, best of {reps})"}
+
+
 # ---------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -261,14 +306,16 @@ def main():
     ap.add_argument("--config", default=os.environ.get("SPB_BENCH_CONFIG", "c4"),
                     choices=sorted(CONFIGS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--gather", default=os.environ.get("SPB_GATHER", "tma"),
-                    choices=["tma", "win", "csr"],
-                    help="stage-1 kernel: TMA-staged tiles, register windows (f64) or CSR")
+    ap.add_argument("--gather", default=os.environ.get("SPB_GATHER", "tmem"),
+                    choices=["tmem", "tma", "csr"],
+                    help="stage-1 kernel: tensor-memory windows (f64; f32 falls back to tma), "
+                         "TMA-staged tiles or CSR")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     os.environ["SPB_GATHER"] = args.gather
+    gather = "tma" if (args.gather == "tmem" and args.dtype != "f64") else args.gather
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -320,24 +367,11 @@ def main():
     gather_events = []
 
     def timed_order(prev, cur, total, b_lo, b_hi):
-        t = sx.t
-        c32, sp = _lib.I32(t.dtype), _lib.stream_ptr()
         cst = torch.cuda.current_stream()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(cst)
-        if t.win_recs is not None and args.gather == "win":
-            _lib.call("spb_exchange_gather_window", prev, sx.g, t.win_ptr, t.win_recs,
-                      sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands,
-                      b_lo, b_hi, sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad,
-                      exchange.window_arg(t), c32, sp)
-        elif args.gather != "csr":
-            _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs,
-                      sx.cta_order(), t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
-                      sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32, sp)
-        else:
-            _lib.call("spb_exchange_gather", prev, sx.g, t.seg_ptr, t.src, t.wgt, t.dly,
-                      t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi,
-                      sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, c32, sp)
+        exchange.launch_gather(sx.t, prev, sx.g, sx.cta_order(), sx.n_alloc, b_lo, b_hi,
+                               sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, kind=gather)
         ev1.record(cst)
         gather_events.append((ev0, ev1))
         sx._mix(cur, total, b_lo, b_hi)
@@ -377,80 +411,127 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = x_per_step / (ms_per_step * 1e-3)
 
-    # -- roofline of the dominant kernel (k_gather), this rank's share ----------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-    except Exception:  # noqa: BLE001
-        pass
+    # -- roofline of the dominant kernel (stage-1 gather), this rank's share ----------
+    peaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
-    # this rank's share of the directed pairs (shards are balanced by dealing the
-    # receiver tiles round-robin, so the patch share is the pair share up to noise)
-    share = 1.0 / world
-    # algorithmic bytes per pair.bin exchange = B*(1+2D)*sizeof; one gather
-    # launch processes this rank's directed pairs x T bins of one order
+    share = 1.0 / world     # shards are balanced by dealing the receiver tiles round-robin
+    # SURVEY 8(d) algorithmic bytes per pair.bin exchange = B*(1+2D)*sizeof (the reference's
+    # dense-tilde formulation); one gather launch processes this rank's directed pairs x T
     alg_bytes_launch = (2.0 * n_pairs * share * n_samples * n_band * (1 + 2 * n_dir) * esize
                         / band_launches)
     gather_avg_ms = float(np.mean(gather_ms)) if gather_ms else float("nan")
-    achieved = alg_bytes_launch / (gather_avg_ms * 1e-3) / 1e9
-    # executed FMAs of the factored kernel: directed pairs x B x T_pad per order
-    # (tiled kernel: one FMA row per non-empty record slot = per kept directed pair)
-    fma_launch = float(tables.src.numel()) * share * n_band * sx.t_pad / band_launches
-    fma_tflops = 2.0 * fma_launch / (gather_avg_ms * 1e-3) / 1e12
+    alg_gbs = alg_bytes_launch / (gather_avg_ms * 1e-3) / 1e9
+    # FMAs of the factored kernel per launch.  useful: one per (kept directed pair, band,
+    # bin); executed: what the records make the pipe do (8 receiver slots per record, empty
+    # slots multiply by zero, the time axis is rounded up to the CTA's bin count)
+    t_exec = -(-sx.t_pad // 512) * 512 if gather == "tmem" else sx.t_pad
+    useful_fma = float(tables.src.numel()) * share * n_band * n_samples / band_launches
+    exec_fma = (float(tables.n_records) * (1.0 if world == 1 else share) * 8 * n_band * t_exec
+                / band_launches) if gather != "csr" else useful_fma * sx.t_pad / n_samples
+    if world > 1 and tables.n_records:          # this rank's records, counted exactly
+        ptr = tables.tile_ptr.view(-1)
+        n_blocks = -(-tables.n_patches // 8)
+        cnt = (ptr[1:] - ptr[:-1]).view(tables.n_classes, n_blocks)
+        mine = int(cnt[:, sx.j_lo // 8:-(-sx.j_hi // 8)].sum().item())
+        exec_fma = float(mine) * 8 * n_band * t_exec / band_launches
+    exec_tflops = 2.0 * exec_fma / (gather_avg_ms * 1e-3) / 1e12
+    pipe = measure_fma_peak(code, dev)
     traffic = None
     try:
         tr = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
-        traffic = tr.get(f"{args.config}/{args.dtype}/{args.gather}", {}).get("bytes")
+        traffic = tr.get(f"{args.config}/{args.dtype}/{gather}", {}).get("bytes")
         if traffic is not None and world > 1:
             traffic = None                      # captured at 1 GPU only
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic,
-                "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0,
-                "kernel": ("k_gather_win" if tables.win_recs is not None and
-                           args.gather == "win" else
-                           "k_gather" if args.gather == "csr" else "k_gather_tma"),
-                "peak_source": peak_src, "avg_launch_ms": gather_avg_ms,
-                "launches_timed": len(gather_ms),
-                "share_of_step": sum(gather_ms) / max(elapsed_ms, 1e-9),
-                "executed_fma_tflops": fma_tflops,
-                "fma_pipe_nominal_tflops": 37.0 if code == _lib.F64 else 75.0,
-                "algorithmic_bytes_per_launch": alg_bytes_launch,
-                "binding_resource": "L1/shared-memory operand path (128 B/clk/SM): one "
-                                    "shifted operand per FMA; see profiles/ and DESIGN.md 3.1",
-                "note": "algorithmic bytes are those of the reference's dense-tilde "
-                        "formulation; the factored kernel moves far fewer, so frac can "
-                        "exceed 1 (see DESIGN.md)"}
+    kernel = {"tmem": "k_gather_tmem", "tma": "k_gather_tma", "csr": "k_gather"}[gather]
+    roofline = {
+        # the gather is bound by its FMA pipe and the operand path that feeds it, not by HBM
+        # (DRAM traffic is a few % of the HBM peak, see `traffic` and profiles/); the
+        # north-star's HBM formulation is kept below as `hbm_algorithmic`
+        "bound": "fp64" if code == _lib.F64 else "fp32",
+        "achieved": exec_tflops, "peak": pipe["tflops"], "unit": "TFLOP/s",
+        "frac": exec_tflops / pipe["tflops"], "traffic": traffic,
+        "peak_source": pipe["how"], "kernel": kernel,
+        "avg_launch_ms": gather_avg_ms, "launches_timed": len(gather_ms),
+        "share_of_step": sum(gather_ms) / max(elapsed_ms, 1e-9),
+        "executed_fma_per_launch": exec_fma, "useful_fma_per_launch": useful_fma,
+        "useful_tflops": 2.0 * useful_fma / (gather_avg_ms * 1e-3) / 1e12,
+        "frac_useful": 2.0 * useful_fma / (gather_avg_ms * 1e-3) / 1e12 / pipe["tflops"],
+        "record_slot_fill": float(tables.src.numel()) / max(1.0, 8.0 * tables.n_records),
+        "fma_pipe_nominal_tflops": 37.0 if code == _lib.F64 else 75.0,
+        "hbm_algorithmic": {
+            "bytes_per_launch": alg_bytes_launch, "achieved": alg_gbs, "peak": hbm_peak,
+            "unit": "GB/s", "frac": alg_gbs / hbm_peak, "frac_nominal_8tbs": alg_gbs / 8000.0,
+            "peak_source": ("measured (MEASURED_PEAKS.json hbm_gbs)" if peaks
+                            else "fallback 6650 GB/s"),
+            "note": "SURVEY 8(d): bytes of the reference's dense-tilde formulation, "
+                    "B*(1+2D)*sizeof per pair.bin; the factored kernel moves far fewer, so "
+                    "this fraction can exceed 1 and is not a utilisation"},
+        "dram_frac_of_hbm_peak": (traffic / (gather_avg_ms * 1e-3) / 1e9 / hbm_peak
+                                  if traffic else None)}
 
-    # -- end to end through the public operator with HOST buffers ---------------------
-    e2e = None
+    # -- end to end with HOST buffers: E0 / distances in pinned host memory -> device, K
+    # orders, full ETC -> pinned host.  One GPU: through the public operator
+    # exchange.energy_exchange_host; sharded: every rank uploads the inputs (each needs all
+    # senders), runs its receiver shard, rank 0 reads the gathered ETC back
+    tdt = _lib.torch_dtype(code)
+    e0_host = rad._e0_dev.cpu().pin_memory()
+    d0_host = rad._d0_dev.cpu().pin_memory()
+    n, d, b = e0_host.shape
+    out_host = (torch.empty((n, d, b, n_samples), dtype=tdt).pin_memory()
+                if rank == 0 else None)
     if world == 1:
-        e0_host = rad._e0_dev.cpu().pin_memory()
-        d0_host = rad._d0_dev.cpu().pin_memory()
-        n, d, b = e0_host.shape
-        out_host = torch.empty((n, d, b, n_samples), dtype=_lib.torch_dtype(code)).pin_memory()
-        ws = exchange.ExchangeWorkspace(tables, n_samples, dev)
-
         def e2e_step():
             exchange.energy_exchange_host(tables, e0_host, d0_host, SPEED_OF_SOUND, DT,
-                                          n_samples, orders, out_host, workspace=ws)
-        for _ in range(2):
-            e2e_step()
-        torch.cuda.synchronize()
-        n_e2e = max(2, min(args.steps, 5))
-        t1 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t1) / n_e2e
-        e2e = {"value": x_per_step / e2e_s, "unit": "pair*bin exchanges/s",
-               "h2d_bytes_per_step": int(e0_host.numel() * 8 + d0_host.numel() * 8),
-               "d2h_bytes_per_step": int(out_host.numel() * esize),
-               "ms_per_step": e2e_s * 1e3,
-               "api": "sparrowpy_b200.exchange.energy_exchange_host (host E0/d0 in pinned "
-                      "memory -> device, K orders, full ETC -> pinned host)"}
+                                          n_samples, orders, out_host)
+        api = ("sparrowpy_b200.exchange.energy_exchange_host (host E0/d0 in pinned memory "
+               "-> device, K orders, full ETC -> pinned host)")
+    else:
+        sx.compute = sx._cuda_order
+
+        def e2e_step():
+            e0 = e0_host.to(dev, non_blocking=True).to(tdt)
+            d0 = d0_host.to(dev, non_blocking=True)
+            sx.init(e0, bake.delay_bins(d0, SPEED_OF_SOUND, DT))
+            hist = sx.run(orders)
+            if rank == 0:
+                out_host.copy_(hist.dense())
+        api = ("host E0/d0 (pinned) -> every rank's device, distributed.ShardedExchange "
+               "init + run (E_total all-gathered), full ETC -> rank 0's pinned host")
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    n_e2e = max(2, min(args.steps, 5))
+    t1 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t1) / n_e2e
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e = {"value": x_per_step / e2e_s, "unit": "pair*bin exchanges/s",
+           "h2d_bytes_per_step": int(e0_host.numel() * 8 + d0_host.numel() * 8) * world,
+           "d2h_bytes_per_step": int(n * d * b * n_samples * esize),
+           "ms_per_step": e2e_s * 1e3, "api": api}
+
+    # -- result evidence: checksum of the ETC and, when sharded, bit-equality with the
+    # single-GPU schedule run on rank 0's device with the same tables
+    result = None
+    if rank == 0:
+        result = {"etc_checksum": float(out_host.double().sum()),
+                  "etc_abs_max": float(out_host.abs().max())}
+        if world > 1:
+            one = distributed.ShardedExchange(tables, n_samples, dev, local=True)
+            one.init(e0_host.to(dev).to(tdt), bake.delay_bins(d0_host.to(dev), SPEED_OF_SOUND, DT))
+            single = one.run(orders).dense()
+            result["equals_single_gpu_bitwise"] = bool(
+                torch.equal(single.cpu(), out_host))
+            result["single_gpu_checksum"] = float(single.double().sum())
+            del one, single
+    barrier()
 
     # -- CPU baseline on the host cores (rank 0, N = 1 only) ----------------------------
     cpu = None
@@ -468,25 +549,20 @@ def main():
             "seconds_per_etc": ms_per_step * 1e-3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic", "gpu_launches": int(launches_per_step * args.steps),
-            "config": {"workload": cfg["desc"], "name": args.config,
-                       "n_patches": rad.n_patches, "visible_pairs": n_pairs,
-                       "directed_pairs_kept": int(tables.src.numel()),
-                       "tile_records": int(tables.n_records), "gather": args.gather,
-                       "record_window": int(tables.win_w),
-                       "n_directions": n_dir, "n_bands": n_band, "n_samples": n_samples,
-                       "reflection_orders": orders,
-                       "exchanges_per_etc": x_per_step,
-                       "l2": "inputs larger than L2" if
-                       rad.n_patches * n_dir * n_band * sx.ld * esize > 126e6 * 2
-                       else "working set fits L2 (small config, no flush)",
-                       "parallelism": (f"receiver shards x{world}, exchange: {sx.comm}"
-                                       if world > 1 else "1 GPU")},
+            "config": workload_config(cfg, args.config, rad.n_patches, n_pairs, n_dir, n_band,
+                                      args.dtype),
+            "run": {"gather": gather, "kernel": kernel,
+                    "directed_pairs_kept": int(tables.src.numel()),
+                    "tile_records": int(tables.n_records),
+                    "record_window": int(tables.win_w),
+                    "parallelism": (f"receiver shards x{world}, exchange: {sx.comm}"
+                                    if world > 1 else "1 GPU")},
             "clocks": clocks.summary(), "roofline": roofline,
         }
         if bake_info:
             line["bake"] = bake_info
-        if e2e:
-            line["e2e"] = e2e
+        line["e2e"] = e2e
+        line["result"] = result
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -675,8 +751,11 @@ def run_reference(args, cfg, rank, world, log):
         return
     rad = build_scene(cfg, "f64")
     torch.cuda.synchronize()
-    threads = orc.max_threads()
+    # thread count set explicitly (torchrun exports OMP_NUM_THREADS=1; the oracle's
+    # `num_threads` clause does not depend on it): every core this process may run on
+    threads = max(1, len(os.sched_getaffinity(0)))
     n_pairs = int(rad._baked["pairs"].shape[0])
+    n_dir, n_band = int(rad._baked["coef"].shape[1]), int(rad._baked["coef"].shape[2])
     orders = cfg["orders"]
     x_per_step = 2.0 * n_pairs * cfg["n_samples"] * orders
     budget = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
@@ -687,6 +766,7 @@ def run_reference(args, cfg, rank, world, log):
         if k >= args.warmup:
             vals.append(res["value"])
     value = float(np.mean(vals)) if vals else float("nan")
+    one = cpu_exchange_rate(rad, cfg, n_threads=1, budget_s=6.0, log=log)
     line = {
         "impl": "reference",
         "metric": "patch-pair*time-bin exchanges/s (energy exchange, s per ETC alongside)",
@@ -695,15 +775,18 @@ def run_reference(args, cfg, rank, world, log):
         "ms_per_step": x_per_step / value * 1e3 if value == value else None,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": cfg["desc"], "name": args.config, "n_patches": rad.n_patches,
-                   "visible_pairs": n_pairs, "reflection_orders": orders},
+        "config": workload_config(cfg, args.config, rad.n_patches, n_pairs, n_dir, n_band,
+                                  "f64"),
         "cpu_baseline": {"value": value, "unit": "pair*bin exchanges/s", "cores": threads,
-                         "kind": "port", "sample": res["sample"] if res else ""},
+                         "kind": "port", "sample": res["sample"] if res else "",
+                         "value_1core": one["value"],
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": value, "unit": "pair*bin exchanges/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "note": "oracle port of _energy_exchange (time-sliced over all host threads, "
                 "bit-identical to the serial reference order); the reference itself is "
-                "single-threaded here (RadiosityFast.py:1396)",
+                "single-threaded here (RadiosityFast.py:1396) -- value_1core is the like-for-"
+                "like figure; the scene is baked by the CUDA path (inputs only, not timed)",
     }
     print(json.dumps(line), flush=True)
 

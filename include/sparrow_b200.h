@@ -303,6 +303,13 @@ int spb_probe_basic_visibility(const double *a, const double *b, const void *blo
                                int64_t count, uint8_t *visible, uint8_t *in_a, uint8_t *in_b,
                                void *stream);
 
+/* Measurement probe (no reference counterpart): launches a register-only FMA kernel of
+ * `n_blocks` x 256 threads x 8 chains x `iters` FMAs in `dtype` and returns the flops it
+ * will execute; the caller times it with CUDA events to obtain the FMA-pipe peak the
+ * compute-bound kernels are reported against.  `scratch`: >= 8 device bytes. */
+int spb_fma_peak(int dtype, int64_t iters, int64_t n_blocks, void *scratch,
+                 double *flops_launched, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

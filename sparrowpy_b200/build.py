@@ -23,6 +23,7 @@ SOURCES = [
     ("exchange_tma.cu", []),
     ("exchange_tmem.cu", []),
     ("bake.cu", ["--fmad=false"]),
+    ("peak.cu", []),
 ]
 
 

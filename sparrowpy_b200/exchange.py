@@ -525,12 +525,14 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
 
 
 def collect_patchwise(hist, rdir, shift, scale):
-    """Per-patch histograms at each receiver, (R, N, B, T)
-    (``collect_energy_receiver_patchwise``, RadiosityFast.py:660-752)."""
+    """Per-patch histograms at each receiver, (R, N, B, T) -- (S, R, N, B, T) for a batch
+    of sources (``collect_energy_receiver_patchwise``, RadiosityFast.py:660-752)."""
     n_rcv = rdir.shape[0]
     tdt = hist.data.dtype
     code = _lib.dtype_code(tdt)
     rdir, shift, scale = (hist.to_internal(x, 1) for x in (rdir, shift, scale))
+    if hist.n_sources is not None:          # the same receiver factors for every source
+        scale = scale.repeat(1, 1, hist.n_sources)
     out = torch.empty((n_rcv, hist.n_patches, hist.n_bands, hist.n_samples), dtype=tdt,
                       device=hist.data.device)
     _lib.call("spb_collect_patchwise", hist.data, rdir.contiguous(), shift.contiguous(),
@@ -539,6 +541,9 @@ def collect_patchwise(hist, rdir, shift, scale):
               _lib.stream_ptr())
     if hist.rank is not None:
         out = out.index_select(1, hist.rank)
+    if hist.n_sources is not None:          # (S, R, N, B, T)
+        r, n = out.shape[:2]
+        out = out.reshape(r, n, hist.n_sources, -1, hist.n_samples).permute(2, 0, 1, 3, 4)
     return out
 
 

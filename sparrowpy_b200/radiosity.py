@@ -61,9 +61,10 @@ class DirectionalRadiosityFast:
 
         self._frequencies = None if frequencies is None else np.array(frequencies)
         self._brdf = None if brdf is None else [np.array(b) for b in brdf]
-        self._brdf_index = brdf_index
-        self._brdf_incoming_directions = brdf_incoming_directions
-        self._brdf_outgoing_directions = brdf_outgoing_directions
+        self._brdf_index = (None if brdf_index is None
+                            else np.atleast_1d(np.array(brdf_index, dtype=np.int64)))
+        self._brdf_incoming_directions = _object_array(brdf_incoming_directions)
+        self._brdf_outgoing_directions = _object_array(brdf_outgoing_directions)
         self._air_attenuation = (None if air_attenuation is None
                                  else np.array(air_attenuation))
         self._speed_of_sound = None if speed_of_sound is None else float(speed_of_sound)
@@ -220,7 +221,6 @@ class DirectionalRadiosityFast:
     def bake_geometry(self):
         """Bake the geometry: visibility, form factors, BRDF direction tables."""
         g = self._geom()
-        dev = self._device
         # blockers = the patches themselves (RadiosityFast.py:374-375); grouped by wall
         # the conjunction over blockers is evaluated hierarchically (same result)
         if os.environ.get("SPB_VISIBILITY", "grouped") == "brute":
@@ -230,6 +230,17 @@ class DirectionalRadiosityFast:
                                               self._patch_to_wall_ids)
         pairs = bake.visible_pairs(vis)
         ff, _ = bake.form_factors(g["points"], g["normal"], g["area"], pairs)
+        self._bake_pairs(vis, pairs, ff)
+        self._tables = None
+        for k in ("visibility_matrix", "visible_patches", "form_factors",
+                  "form_factors_tilde", "patch_2_brdf_outgoing_index"):
+            self._host[k] = None
+
+    def _bake_pairs(self, vis, pairs, ff):
+        """Per-pair device tables behind ``form_factors_tilde`` (RadiosityFast.py:403-433,
+        :1234-1272) from the visibility matrix, the visible pairs and their form factors."""
+        g = self._geom()
+        dev = self._device
         with_brdf = self._brdf_incoming_directions is not None
         if with_brdf:
             vi, vo, brdf, bidx = self._brdf_tables()
@@ -260,10 +271,6 @@ class DirectionalRadiosityFast:
             cls=cls_idx, coef=torch.from_numpy(np.ascontiguousarray(coef)).to(dev),
             sender=sender, receiver=receiver, ff_dir=ff_dir, with_brdf=with_brdf,
             n_out=n_out, n_bins=n_bins)
-        self._tables = None
-        for k in ("visibility_matrix", "visible_patches", "form_factors",
-                  "form_factors_tilde", "patch_2_brdf_outgoing_index"):
-            self._host[k] = None
 
     # ------------------------------------------------------------------
     # source: RadiosityFast.py:436-522
@@ -372,6 +379,37 @@ class DirectionalRadiosityFast:
             self._tables = (key, tables)
         return self._tables[1]
 
+    def _resume(self):
+        """Rebuild the device state that a restored checkpoint (``from_dict``) holds on the
+        host only, so that the simulation continues at whatever stage it was saved
+        (reference: tests/test_DirectionalRadiosityFast.py:72-125, ``cls(**input_dict)``
+        RadiosityFast.py:882-886)."""
+        h = self._host
+        dev = self._device
+        if (self._baked is None and h["visible_patches"] is not None
+                and h["form_factors"] is not None):
+            pairs = np.asarray(h["visible_patches"], dtype=np.int64).reshape(-1, 2)
+            ffm = np.asarray(h["form_factors"], dtype=float)
+            ff = np.ascontiguousarray(ffm[pairs[:, 0], pairs[:, 1]])
+            vis = h["visibility_matrix"]
+            if vis is None:
+                vis = np.zeros((self.n_patches, self.n_patches), dtype=bool)
+                vis[pairs[:, 0], pairs[:, 1]] = True
+            keep = {k: h[k] for k in ("visibility_matrix", "visible_patches", "form_factors",
+                                      "form_factors_tilde", "patch_2_brdf_outgoing_index")}
+            self._bake_pairs(
+                torch.from_numpy(np.ascontiguousarray(vis).astype(np.uint8)).to(dev),
+                torch.from_numpy(pairs.astype(np.int32)).to(dev).contiguous(),
+                torch.from_numpy(ff).to(dev))
+            self._tables = None
+            h.update(keep)                  # the restored arrays stay what was restored
+        if (self._e0_dev is None and h["energy_init_source"] is not None
+                and h["distance_patches_to_source"] is not None):
+            self._e0_dev = torch.from_numpy(np.ascontiguousarray(
+                h["energy_init_source"], dtype=float)).to(dev)
+            self._d0_dev = torch.from_numpy(np.ascontiguousarray(
+                h["distance_patches_to_source"], dtype=float)).to(dev)
+
     def calculate_energy_exchange(
             self, speed_of_sound, etc_time_resolution, etc_duration,
             max_reflection_order=-1, recalculate=False):
@@ -380,6 +418,7 @@ class DirectionalRadiosityFast:
         have_result = self._hist is not None or \
             self._host["energy_exchange_etc"] is not None
         if not have_result or recalculate:
+            self._resume()
             if self._e0_dev is None:
                 raise _lib.SparrowB200Error(
                     "init_source_energy must be called before calculate_energy_exchange")
@@ -660,6 +699,15 @@ class DirectionalRadiosityFast:
                 dict_out[key] = value.tolist()
         return dict_out
 
+    def __eq__(self, other):
+        """Equality of two objects = equality of their ``to_dict()`` (RadiosityFast.py:875-879;
+        the reference uses deepdiff, here a numpy-aware recursive comparison)."""
+        if not isinstance(other, DirectionalRadiosityFast):
+            return False
+        return _deep_equal(self.to_dict(), other.to_dict())
+
+    __hash__ = None
+
     @classmethod
     def from_dict(cls, input_dict):
         """Create an object from a dictionary (resume from a checkpoint)."""
@@ -760,3 +808,47 @@ def _rotate_coords_to_normal(wall_normal, wall_up_vector, sources, receivers):
         weights = getattr(c, "weights", None)
         out.append(pyfar_shim.Coordinates.from_cartesian(xyz, weights=weights))
     return out[0], out[1]
+
+
+def _object_array(items):
+    """BRDF direction lists as the reference keeps them: 1-D object arrays of Coordinates
+    (RadiosityFast.py:789-792), whatever sequence a checkpoint handed in."""
+    if items is None:
+        return None
+    out = np.empty(len(items), dtype=object)
+    for i, item in enumerate(items):
+        out[i] = item
+    return out
+
+
+def _deep_equal(a, b):
+    """Recursive equality of checkpoint values: dicts, sequences, numpy arrays, Coordinates
+    (compared by cartesian points and weights) and scalars."""
+    if isinstance(a, dict) or isinstance(b, dict):
+        return (isinstance(a, dict) and isinstance(b, dict) and a.keys() == b.keys()
+                and all(_deep_equal(a[k], b[k]) for k in a))
+    if isinstance(a, _COORD_TYPES) or isinstance(b, _COORD_TYPES):
+        if not (isinstance(a, _COORD_TYPES) and isinstance(b, _COORD_TYPES)):
+            return False
+        wa, wb = getattr(a, "weights", None), getattr(b, "weights", None)
+        return (_deep_equal(np.asarray(a.cartesian), np.asarray(b.cartesian))
+                and _deep_equal(wa, wb))
+    if isinstance(a, str) or isinstance(b, str):
+        return isinstance(a, str) and isinstance(b, str) and a == b
+    if a is None or b is None:
+        return a is None and b is None
+    seq = (list, tuple, np.ndarray)
+    if isinstance(a, seq) or isinstance(b, seq):
+        if not (isinstance(a, seq) and isinstance(b, seq)):
+            return False
+        aa = a if isinstance(a, np.ndarray) else None
+        bb = b if isinstance(b, np.ndarray) else None
+        if (aa is None or aa.dtype != object) and (bb is None or bb.dtype != object):
+            try:
+                aa, bb = np.asarray(a), np.asarray(b)
+                if aa.dtype != object and bb.dtype != object:
+                    return aa.shape == bb.shape and bool(np.array_equal(aa, bb))
+            except ValueError:            # ragged: element by element below
+                pass
+        return len(a) == len(b) and all(_deep_equal(x, y) for x, y in zip(a, b))
+    return bool(a == b)

@@ -79,3 +79,35 @@ def test_no_cpu_fallback():
     rad = sp.DirectionalRadiosityFast.from_polygon(sp.testing.shoebox_room_stub(1, 1, 1), 1.0)
     with pytest.raises(SparrowB200Error, match="no CPU fallback"):
         rad.bake_geometry()
+
+
+def test_equality_and_checkpoint_of_unbaked_objects():
+    """``__eq__`` = equality of ``to_dict()`` (RadiosityFast.py:875-879) and the first two
+    stages of the reference's test_io (tests/test_DirectionalRadiosityFast.py:23-48) --
+    host-only state, so this runs without a GPU."""
+    import numpy as np
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    walls = sp.testing.shoebox_room_stub(1, 1, 1)[:2]
+    rad = sp.DirectionalRadiosityFast.from_polygon(walls, 1)
+    out = sp.DirectionalRadiosityFast.from_dict(rad.to_dict())
+    assert out == rad and not (out != rad)
+    assert rad != 5 and rad != None  # noqa: E711
+    freqs = [1000]
+    rad.set_wall_brdf(np.arange(len(walls)), pf.FrequencyData(np.ones_like(freqs), freqs),
+                      pf.Coordinates(0, 0, 1, weights=1), pf.Coordinates(0, 0, 1, weights=1))
+    assert out != rad
+    out = sp.DirectionalRadiosityFast.from_dict(rad.to_dict())
+    assert out == rad
+    assert isinstance(out._brdf_index, np.ndarray) and out._brdf_index.dtype == np.int64
+    assert out._brdf_incoming_directions.dtype == object
+    rad.set_air_attenuation(pf.FrequencyData(np.ones_like(freqs), freqs))
+    assert out != rad
+    out = sp.DirectionalRadiosityFast.from_dict(rad.to_dict())
+    assert out == rad
+    # a different patch size is a different object
+    assert sp.DirectionalRadiosityFast.from_polygon(walls, 0.5) != rad
+    # a resumed object accepts further BRDF assignments
+    out.set_wall_brdf(np.array([1]), pf.FrequencyData(np.ones_like(freqs), freqs),
+                      pf.Coordinates(0, 0, 1, weights=1), pf.Coordinates(0, 0, 1, weights=1))
+    assert list(out._brdf_index) == [0, 1]

@@ -160,6 +160,95 @@ def test_checkpoint_roundtrip_and_resume():
     assert again.n_patches == fresh.n_patches and again._form_factors is None
 
 
+def test_io_within_simulation_resumes_at_every_stage():
+    """Mirror of the reference's test_io_within_simulation / test_io (tests/
+    test_DirectionalRadiosityFast.py:23-125): a checkpoint taken after set-up, after the
+    bake, after the source and after the exchange continues to the same ETC, and the
+    round-tripped object compares equal (``__eq__``, RadiosityFast.py:875-879)."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    g = load_golden("scene_directional")
+    c, dt, dur, order = float(g["speed_of_sound"]), float(g["dt"]), float(g["duration"]), 3
+    src = pf.Coordinates(*g["source"])
+    rcv = pf.Coordinates.from_cartesian(g["receivers"])
+    walls = [sp.Polygon(p, u, n) for p, u, n in
+             zip(g["walls_points"], g["walls_up"], g["walls_normal"])]
+    rad = sp.DirectionalRadiosityFast.from_polygon(walls, float(g["patch_size"]))
+    rt = sp.DirectionalRadiosityFast.from_dict(rad.to_dict())
+    assert rt == rad and not (rt != rad)
+    coords = pf.Coordinates.from_cartesian(g["brdf_dirs"], weights=g["brdf_weights"])
+    for m in range(g["brdf"].shape[0]):
+        rad.set_wall_brdf(np.nonzero(g["brdf_index"] == m)[0],
+                          pf.FrequencyData(g["brdf"][m] / np.pi, g["frequencies"]),
+                          coords, coords)
+    rad.set_air_attenuation(pf.FrequencyData(g["air_attenuation"], g["frequencies"]))
+    assert rt != rad
+    stage0 = sp.DirectionalRadiosityFast.from_dict(rad.to_dict())      # before the bake
+    assert stage0 == rad
+    rad.bake_geometry()
+    stage1 = sp.DirectionalRadiosityFast.from_dict(rad.to_dict())      # baked
+    assert stage1 == rad and stage0 != rad
+    rad.init_source_energy(src)
+    stage2 = sp.DirectionalRadiosityFast.from_dict(rad.to_dict())      # baked + source
+    assert stage2 == rad
+    rad.calculate_energy_exchange(c, dt, dur, max_reflection_order=order)
+    stage3 = sp.DirectionalRadiosityFast.from_dict(rad.to_dict())      # finished
+    assert stage3 == rad and stage2 != rad
+    assert rad != "something else"
+    mono = rad.collect_energy_receiver_mono(rcv).time
+
+    stage0.bake_geometry()
+    stage0.init_source_energy(src)
+    stage1.init_source_energy(src)
+    for obj in (stage0, stage1, stage2, stage3):
+        obj.calculate_energy_exchange(c, dt, dur, max_reflection_order=order, recalculate=True)
+        assert rel_err(obj._energy_exchange_etc, rad._energy_exchange_etc) < 1e-13
+        assert rel_err(obj.collect_energy_receiver_mono(rcv).time, mono) < 1e-12
+    # a resumed object accepts further BRDF assignments (brdf_index is an array again)
+    stage3.set_wall_brdf(np.array([0]), pf.FrequencyData(g["brdf"][0] / np.pi, g["frequencies"]),
+                         coords, coords)
+    assert int(stage3._brdf_index[0]) == len(stage3._brdf) - 1
+
+
+def test_patchwise_collection_of_a_source_batch():
+    """collect_energy_receiver_patchwise after init_source_energy_batch: (S, R, N, B, T),
+    equal to the single-source results and summing to the mono ETC."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    g = load_golden("scene_directional")
+    srcs = np.array([g["source"], [0.6, 1.5, 0.4]])
+    rcv = pf.Coordinates.from_cartesian(g["receivers"])
+    c, dt, dur, order = float(g["speed_of_sound"]), float(g["dt"]), float(g["duration"]), 2
+    walls = [sp.Polygon(p, u, n) for p, u, n in
+             zip(g["walls_points"], g["walls_up"], g["walls_normal"])]
+
+    def fresh():
+        r = sp.DirectionalRadiosityFast.from_polygon(walls, float(g["patch_size"]))
+        coords = pf.Coordinates.from_cartesian(g["brdf_dirs"], weights=g["brdf_weights"])
+        for m in range(g["brdf"].shape[0]):
+            r.set_wall_brdf(np.nonzero(g["brdf_index"] == m)[0],
+                            pf.FrequencyData(g["brdf"][m] / np.pi, g["frequencies"]),
+                            coords, coords)
+        r.set_air_attenuation(pf.FrequencyData(g["air_attenuation"], g["frequencies"]))
+        r.bake_geometry()
+        return r
+
+    batch = fresh()
+    batch.init_source_energy_batch(pf.Coordinates.from_cartesian(srcs))
+    batch.calculate_energy_exchange(c, dt, dur, max_reflection_order=order)
+    pw = batch.collect_energy_receiver_patchwise(rcv).time
+    mono = batch.collect_energy_receiver_mono(rcv).time
+    n_rcv = np.atleast_2d(g["receivers"]).shape[0]
+    assert pw.shape == (2, n_rcv, batch.n_patches) + mono.shape[2:]
+    assert rel_err(pw.sum(axis=2), mono) < 1e-12
+    single = fresh()
+    for s in range(2):
+        single.init_source_energy(pf.Coordinates(*srcs[s]))
+        single.calculate_energy_exchange(c, dt, dur, max_reflection_order=order,
+                                         recalculate=True)
+        assert rel_err(pw[s], single.collect_energy_receiver_patchwise(rcv).time) < 1e-13
+
+
 def test_direct_sound_added_at_floor_delay():
     """collect_energy_receiver_mono(direct_sound=True) (RadiosityFast.py:594-657)."""
     import sparrowpy_b200 as sp

@@ -52,7 +52,7 @@ def device_tables(g, out, dtype, n_samples):
                                       n, n_samples, dtype)
 
 
-@pytest.mark.parametrize("gather", ["tma", "csr"])
+@pytest.mark.parametrize("gather", ["tmem", "tma", "csr"])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("name", SCENES)
 def test_exchange_matches_oracle(oracle, name, dtype, gather, monkeypatch):
@@ -156,7 +156,7 @@ def test_tiled_and_csr_gather_agree_on_ragged_lists():
     cls[receiver % 5 == 0] = 1                                # leave some segments empty
     coef = torch.rand((c, d, b), generator=gen, dtype=torch.float64).to(dev)
     tables = exchange.build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n,
-                                        t_len, "f64")
+                                        t_len, "f64", gather="tma")
     t_pad, pad = _lib.exchange_layout(t_len, tables.max_delay, tables.dtype)
     ld = t_pad + pad
     prev = torch.zeros((b * n * d, ld), dtype=torch.float64, device=dev)
@@ -223,9 +223,8 @@ def test_sharded_driver_matches_one_call_api(oracle):
     for _ in range(4):
         for lo, hi in ((lo0, hi0), (lo1, hi1)):
             for b in range(t.n_bands):           # one band at a time, like the pipeline
-                _lib.call("spb_exchange_gather_tiled", prev, sx.g, t.ent_ptr, t.recs, None,
-                          t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b, b + 1,
-                          lo, hi, sx.t_pad, sx.ld, sx.pad, code, st)
+                exchange.launch_gather(t, prev, sx.g, None, sx.n_alloc, b, b + 1, lo, hi,
+                                       sx.t_pad, sx.ld, sx.pad)
                 _lib.call("spb_exchange_mix", sx.g, cur, sx.e_total, t.seg_ptr, t.coef,
                           t.n_patches, sx.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b, b + 1,
                           lo, hi, sx.t_pad, sx.ld, sx.pad, code, st)

@@ -48,22 +48,18 @@ constexpr int kLaneT = 16;                     // consecutive time bins per TMEM
 constexpr int kQuarterT = 32 * kLaneT;         // 512 bins per lane quarter
 constexpr int kBoxArea = 20480;                // bytes reserved for the staged boxes of a record
 constexpr int kBatch = 2;                      // records per pipeline hand-over
-constexpr int kRecSlot = 96;                   // bytes per (TMEM stage, quarter) record copy
-constexpr int kThreads = 512;   // 8 consumer + 4 fill + 1 producer (+ 3 idle) warps; 512 x 128 regs
+constexpr bool kPipeDefault = false;           // software-pipelined consumer loop
+constexpr int kThreads = 512;   // 8 consumer + 4 fill + 4 producer warps; 512 x 128 regs
                                 // at launch = the whole file, so setmaxnreg only re-deals it
-constexpr int kRegsConsumer = 184, kRegsFill = 104, kRegsProducer = 40;
 
 struct alignas(16) WinRecord {
     double w[kR];        // weight per receiver slot
-    uint8_t rel[kR];     // delay - dbase (0..H), 255 = no pair in this slot
+    uint8_t rel[kR];     // TMEM column offset 2 (delay - dbase); 0 (and w = 0) = no pair
+                         // (device encoding, exchange.device_window_records)
     int32_t src;         // sender row = patch * D + outgoing direction
     int32_t dbase;       // even
 };
 static_assert(sizeof(WinRecord) == 80, "record layout");
-// setmaxnreg.inc can only take what setmaxnreg.dec released inside the CTA (a pool that starts
-// empty): the re-deal must not need more registers than the launch allocated
-static_assert(8 * kRegsConsumer + 4 * kRegsFill + 4 * kRegsProducer <= 16 * 128,
-              "register re-deal exceeds the launch allocation (the kernel would hang)");
 
 template <int H>
 struct Cfg {
@@ -121,6 +117,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t *r, uint32_t addr) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
           "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
           "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr));
+}
+// 32 consecutive columns = the 16 doubles a lane needs for one receiver
+__device__ __forceinline__ void tmem_ld32(uint32_t *r, uint32_t addr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
+        "%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+          "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
         : "r"(addr));
 }
 __device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t *r) {
@@ -207,6 +216,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void lds_f64x2(double &a, double &b, uint32_t addr) {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -221,53 +235,92 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) {
     asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 
-// One record of the fill: lane `rb`'s row (C::kChunks 16-byte chunks starting at logical
-// chunk J of its first tensor row) from the swizzled stage into the TMEM stage.  p[j] =
-// address of the lane's tensor row j with the row's swizzle key folded in, so that logical
-// chunk cc of that row is at p[j] ^ (cc << 4).
-// The lane's whole row through the registers at once: all LDS.128 are independent (one
-// shared-memory latency per record), then the fewest power-of-two tcgen05.st.
-template <int H, int J>
-__device__ __forceinline__ void fill_row(const uint32_t (&p)[3], uint32_t taddr) {
+// One record of the fill: the lane's row (C::kChunks 16-byte chunks) from the swizzled
+// stage into the TMEM stage.  The producer picks, per record, the tensor map whose origin
+// makes the lane's row start at chunk 0 of its tensor row, so the chunk addresses are
+// static: p0 / p1 = address of the lane's tensor row / the next one with the row's swizzle
+// key folded in (logical chunk cc of a row is at p ^ (cc << 4)).
+// kPasses = 1: the whole row through the registers at once (one shared-memory latency per
+// record); 2: at most 8 chunks at a time (for a fill warp that runs on 56 registers).
+template <int H, int kPasses>
+__device__ __forceinline__ void fill_row(uint32_t p0, uint32_t p1, uint32_t taddr) {
     using C = Cfg<H>;
-    uint32_t v[C::kCols];
+    constexpr int kFirst = kPasses == 1 ? C::kChunks : (C::kChunks < 8 ? C::kChunks : 8);
+    {
+        uint32_t v[4 * kFirst];
 #pragma unroll
-    for (int i = 0; i < C::kChunks; ++i) {
-        const int lc = i + J;
-        const uint4 x = lds128(p[lc >> 3] ^ (uint32_t)((lc & 7) << 4));
-        v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+        for (int i = 0; i < kFirst; ++i) {
+            const uint4 x = lds128(i < 8 ? p0 ^ (uint32_t)(i << 4) : p1 ^ (uint32_t)((i - 8) << 4));
+            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+        }
+        tmem_store_row<4 * kFirst>(taddr, v);
     }
-    tmem_store_row<C::kCols>(taddr, v);
+    if constexpr (C::kChunks > kFirst) {
+        constexpr int kRest = C::kChunks - kFirst;
+        uint32_t v[4 * kRest];
+#pragma unroll
+        for (int i = 0; i < kRest; ++i) {
+            const uint4 x = lds128(p1 ^ (uint32_t)((i + kFirst - 8) << 4));
+            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+        }
+        tmem_store_row<4 * kRest>(taddr + 4 * kFirst, v);
+    }
 }
 
-template <int H, int B>
+// Tensor maps of the previous-order histogram seen as rows of 16 doubles, one per starting
+// phase: map J has its origin at double 2 J, so a window that starts at double a is the box
+// at row a >> 4 of map (a & 15) >> 1 and lands chunk-aligned in shared memory.
+struct TmapSet {
+    CUtensorMap m[8];
+};
+
+// Register deal per role (setmaxnreg); launch = 16 warps x 128.
+template <bool kPipe>
+struct Regs {
+    static constexpr int kConsumer = kPipe ? 216 : 184;
+    static constexpr int kFill = kPipe ? 56 : 104;
+    static constexpr int kProducer = kPipe ? 24 : 40;
+    // setmaxnreg.inc can only take what setmaxnreg.dec released inside the CTA (a pool that
+    // starts empty): the re-deal must not need more registers than the launch allocated
+    static_assert(8 * kConsumer + 4 * kFill + 4 * kProducer <= 16 * 128,
+                  "register re-deal exceeds the launch allocation (the kernel would hang)");
+};
+
+template <int H, int B, bool kPipe>
 __global__ void __launch_bounds__(kThreads, 1)
-k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
+k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
               const int64_t *__restrict__ ent_ptr, const WinRecord *__restrict__ recs,
               const int32_t *__restrict__ cta_order, int64_t n_patches, int64_t n_alloc,
               int64_t n_blocks, int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t jb_lo,
               int64_t n_jb, int64_t n_classes, int64_t t_pad, int64_t ld, int64_t pad, int qpb,
-              int n_tchunks, int dbg) {
+              int n_tchunks) {
     // Every hand-over of the pipeline (producer -> fill -> consumers) moves a BATCH of B
     // records: the barrier waits, fences and arrivals are a serial chain of a few hundred
     // cycles per hand-over in every role, and per single record that chain, not any
     // bandwidth, bounded the kernel (measured: 480 clk per record with no data moved at all).
     using C = Cfg<H>;
+    using R = Regs<kPipe>;
     constexpr int S = 8 / B;                           // shared-memory stages (of B records)
     constexpr int TS = 512 / (B * C::kCols);           // TMEM stages (of B rows per lane)
-    constexpr int kStage = B * kBoxArea + 1024;        // boxes + the B records
-    constexpr int kSlot = B * kRecSlot;                // per (TMEM stage, quarter)
+    // The records themselves go into a ring of S + TS batches that the consumers read
+    // directly: when the producer refills slot n mod (S + TS) it has seen the fill warps
+    // release the shared-memory stage of batch n - S, which they did after the consumers
+    // released the TMEM stage of batch n - S - TS.
+    constexpr int RS = S + TS;
+    constexpr int kStage = B * kBoxArea;               // staged boxes of one batch
+    constexpr int kRing = RS * B * (int)sizeof(WinRecord);
     static_assert(TS >= 2 && S >= 2, "double buffering");
+    static_assert(kRing % 16 == 0, "ring alignment");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: S x kStage | rec slots [TS][4][B][kRecSlot] | barriers | tmem slot
+    // layout: S x kStage | record ring | barriers | tmem slot
     const uint32_t sm_stages = smem_u32(smem_raw);
-    const uint32_t sm_slots = sm_stages + S * kStage;
-    const uint32_t sm_full = sm_slots + TS * 4 * kSlot;               // smem_full[S]
+    const uint32_t sm_recs = sm_stages + S * kStage;
+    const uint32_t sm_full = sm_recs + kRing;                         // smem_full[S]
     const uint32_t sm_empty = sm_full + 8 * S;                        // smem_empty[S]
     const uint32_t tm_full = sm_empty + 8 * S;                        // tmem_full[TS][4]
     const uint32_t tm_empty = tm_full + 8 * TS * 4;                   // tmem_empty[TS][4]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(
-        smem_raw + S * kStage + TS * 4 * kSlot + 16 * S + 64 * TS);
+        smem_raw + S * kStage + kRing + 16 * S + 64 * TS);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -294,7 +347,7 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
 #pragma unroll
     for (int q = 0; q < 4; ++q) n_act_q += q_active(q) ? 1 : 0;
     for (int s = 0; s < bands_per_cta; ++s) n_act_bands += (band0 + s < b_hi) ? 1 : 0;
-    const int box_rows = 32 * qpb + 2;
+    const int box_rows = 32 * qpb + 1;
     const int box_stride = (box_rows * 128 + 1023) & ~1023;
 
     if (threadIdx.x == 0) {
@@ -320,8 +373,14 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= 12) {
-        // ---------------- producer warp (one working lane) ----------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        // ---------------- producer warps (one working lane each) ----------------
+        // Producer warp p feeds shared-memory stage p: issuing the copies of one batch is a
+        // serial chain of ~1300 cycles in a single thread (barrier wait, expect_tx, address
+        // arithmetic, UTMALDG through the uniform datapath), which with ONE producer warp was
+        // what bounded the whole kernel; four of them run these chains concurrently.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::kProducer));
+        static_assert(S == 4, "one producer warp per shared-memory stage");
+        const int p = warp - 12;
         const uint32_t tx_bytes =
             (uint32_t)(B * (n_act_bands * box_rows * 128 + (int)sizeof(WinRecord)));
         // first double of lane 0's row = a_base + band slot * a_band + src * ld - dbase
@@ -329,59 +388,65 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
         const int64_t a_base = band0 * a_band + pad + t_base - H;
         const WinRecord *rp = recs + e0;
         const int n_rec = n_bat * B;
-        int stage = 0;
+        const uint32_t full = sm_full + 8u * p, empty = sm_empty + 8u * p;
+        const uint32_t st0 = sm_stages + (uint32_t)p * kStage;
         uint32_t phase = 0;
-        for (int e = 0; e < (warp == 12 ? n_rec : 0); e += 32) {    // warps 13..15 idle
+        for (int e = 0; e < n_rec; e += 32) {
+            // (src, dbase) of the next 32 records, one per lane (all four warps read them)
             int32_t s = 0, db = 0;
             if (e + lane < n_rec) { s = rp[e + lane].src; db = rp[e + lane].dbase; }
             const int cnt = min(32, n_rec - e);
-            for (int k = 0; k < cnt; k += B) {
+            for (int k = p * B; k < cnt; k += 4 * B) {     // batches e / B + p, + 4, ...
                 if (lane == 0) {
-                    mbar_wait_a(sm_empty + 8 * stage, phase ^ 1);
+                    mbar_wait_a(empty, phase ^ 1);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                                     sm_full + 8u * stage), "r"(tx_bytes) : "memory");
+                                     full), "r"(tx_bytes) : "memory");
                 }
 #pragma unroll
                 for (int r = 0; r < B; ++r) {
                     const int32_t sk = __shfl_sync(0xffffffffu, s, k + r);
                     const int32_t dk = __shfl_sync(0xffffffffu, db, k + r);
                     if (lane == 0) {
-                        const uint32_t st = sm_stages + (uint32_t)stage * kStage + r * kBoxArea;
+                        const uint32_t st = st0 + r * kBoxArea;
                         int64_t a0 = a_base + (int64_t)sk * ld - dk;
-                        for (int bs = 0; bs < ((dbg & 8) ? 0 : n_act_bands); ++bs, a0 += a_band) {
+                        // every term but dbase + H is a multiple of 16: one map for all bands
+                        const CUtensorMap *map = &tmaps.m[((uint32_t)a0 & 15u) >> 1];
+                        for (int bs = 0; bs < n_act_bands; ++bs, a0 += a_band) {
                             const int32_t row0 = (int32_t)(a0 >> 4);       // tensor row (floor)
                             asm volatile(
                                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
                                 "[%0], [%1, {%2, %3}], [%4];" ::"r"(st + bs * box_stride),
-                                "l"(&tmap), "r"(0), "r"(row0), "r"(sm_full + 8u * stage)
+                                "l"(map), "r"(0), "r"(row0), "r"(full)
                                 : "memory");
                         }
                     }
                 }
-                if (lane == 0)
+                if (lane == 0) {
+                    const int rs = ((e + k) / B) % RS;         // ring slot of this batch
                     asm volatile(
                         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                        ::"r"(sm_stages + (uint32_t)stage * kStage + B * kBoxArea), "l"(rp + e + k),
-                        "r"((uint32_t)(B * sizeof(WinRecord))), "r"(sm_full + 8u * stage)
+                        ::"r"(sm_recs + (uint32_t)(rs * B * (int)sizeof(WinRecord))), "l"(rp + e + k),
+                        "r"((uint32_t)(B * sizeof(WinRecord))), "r"(full)
                         : "memory");
-                if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                phase ^= 1;
             }
         }
     } else if (warp >= 8) {
         // ---------------- fill warps: smem stage -> TMEM stage ----------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsFill));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::kFill));
         const int q = warp - 8;
         if (q_active(q)) {
             const int rb = (q % qpb) * 32 + lane;           // the lane's row inside its box
-            // offset of the lane's tensor rows 0..2 inside a box, swizzle key folded in
-            uint32_t row_off[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                row_off[j] = (uint32_t)((q / qpb) * box_stride + (rb + j) * 128 + (((rb + j) & 7) << 4));
+            // offsets of the lane's tensor row and the next one inside a box, swizzle key
+            // folded in
+            const uint32_t off0 = (uint32_t)((q / qpb) * box_stride + rb * 128 + ((rb & 7) << 4));
+            const uint32_t off1 =
+                (uint32_t)((q / qpb) * box_stride + (rb + 1) * 128 + (((rb + 1) & 7) << 4));
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
             uint32_t st = sm_stages, sfull = sm_full;            // smem_empty = sfull + 8 S
             uint32_t tfull = tm_full + 8 * q;                    // tmem_empty = tfull + 32 TS
-            uint32_t slot = sm_slots + q * kSlot + 8 * lane, tcol = trow;
+            uint32_t tcol = trow;
             int ss = 0, ts = 0;
             uint32_t sphase = 0, tphase = 1;
             for (int e = n_bat; e > 0; --e) {
@@ -389,36 +454,9 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
                 mbar_wait_a(tfull + 32 * TS, tphase);
                 tc_fence_after();
 #pragma unroll
-                for (int r = 0; r < B; ++r) {
-                    const uint32_t rec = st + B * kBoxArea + r * (int)sizeof(WinRecord);
-                    // weights (lanes 0..7) and shifts (lane 8) of the record; the shifts are
-                    // turned into TMEM column offsets 2 * rel (0 for an empty slot)
-                    uint64_t rec_word = 0;
-                    if (lane < 9) rec_word = lds64(rec + 8 * lane);
-                    // 16-byte chunk at which lane 0's row starts inside its first tensor row
-                    const int dbase = (int)lds32(rec + 76);
-                    const int joff = (int)(((uint32_t)(-(dbase + H))) & 15u) >> 1;
-                    if (lane == 8) {
-                        uint32_t lo = (uint32_t)rec_word, hi = (uint32_t)(rec_word >> 32);
-                        lo &= ~__vcmpeq4(lo, 0xffffffffu);
-                        hi &= ~__vcmpeq4(hi, 0xffffffffu);
-                        rec_word = ((uint64_t)(hi + hi) << 32) | (uint64_t)(lo + lo);
-                    }
-                    const uint32_t bx = st + r * kBoxArea;
-                    const uint32_t p[3] = {bx + row_off[0], bx + row_off[1], bx + row_off[2]};
-                    const uint32_t tc0 = tcol + r * C::kCols;
-                    if (!(dbg & 2)) switch (joff) {                // warp-uniform
-                        case 0: fill_row<H, 0>(p, tc0); break;
-                        case 1: fill_row<H, 1>(p, tc0); break;
-                        case 2: fill_row<H, 2>(p, tc0); break;
-                        case 3: fill_row<H, 3>(p, tc0); break;
-                        case 4: fill_row<H, 4>(p, tc0); break;
-                        case 5: fill_row<H, 5>(p, tc0); break;
-                        case 6: fill_row<H, 6>(p, tc0); break;
-                        default: fill_row<H, 7>(p, tc0); break;
-                    }
-                    if (lane < 9) sts64(slot + r * kRecSlot, rec_word);
-                }
+                for (int r = 0; r < B; ++r)
+                    fill_row<H, kPipe ? 2 : 1>(st + r * kBoxArea + off0, st + r * kBoxArea + off1,
+                                               tcol + r * C::kCols);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -428,16 +466,13 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
                 }
                 st += kStage; sfull += 8;
                 if (++ss == S) { ss = 0; sphase ^= 1; st = sm_stages; sfull = sm_full; }
-                tfull += 32; slot += 4 * kSlot; tcol += B * C::kCols;
-                if (++ts == TS) {
-                    ts = 0; tphase ^= 1;
-                    tfull = tm_full + 8 * q; slot = sm_slots + q * kSlot + 8 * lane; tcol = trow;
-                }
+                tfull += 32; tcol += B * C::kCols;
+                if (++ts == TS) { ts = 0; tphase ^= 1; tfull = tm_full + 8 * q; tcol = trow; }
             }
         }
     } else {
         // ---------------- consumer warps ----------------
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R::kConsumer));
         const int q = warp & 3, grp = warp >> 2;
         if (q_active(q)) {
             double acc[4][kLaneT];
@@ -446,25 +481,32 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
 #pragma unroll
                 for (int k = 0; k < kLaneT; ++k) acc[s][k] = 0.0;
             const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * H;
-            const uint32_t slot0 = sm_slots + q * kSlot + 32 * grp;   // this group's weights
-            uint32_t col = col0, slot = slot0;
+            // this group's part of a record in the ring: w[4 grp ..] and the 4 column offsets
+            // (2 x (delay - dbase), 0 for an empty slot) of its receivers
+            const uint32_t rec0 = sm_recs + 32 * grp;
+            uint32_t col = col0, rec = rec0;
             uint32_t tfull = tm_full + 8 * q;                          // tmem_empty = + 32 TS
-            int ts = 0;
+            int ts = 0, rs = 0;
             uint32_t tphase = 0;
-            // Per receiver: two x16 loads, one wait, 16 DFMAs; the two consumer warps of a
-            // scheduler overlap each other's TMEM latency.  Empty slots have w = 0 and read
-            // the window at shift 0 (finite energies, a numerical no-op): no branches.
-            for (int n = n_bat; n > 0; --n) {
-                mbar_wait_a(tfull, tphase);
-                tc_fence_after();
+            // address of the 4 offset bytes of record r: base of the record + 64 + 4 grp
+            // = (rec + r * 80) - 32 grp + 64 + 4 grp
+            auto off_addr = [&](int r) { return rec + r * (int)sizeof(WinRecord) + 64 - 28 * grp; };
+            if constexpr (!kPipe) {
+                // Per receiver: one x32 load, 16 DFMAs; ptxas overlaps the next receiver's
+                // load with the DFMAs as far as the registers allow, and the two consumer
+                // warps of a scheduler overlap each other's TMEM latency.  Empty slots have
+                // w = 0 and read the window at shift 0 (finite energies, a numerical no-op):
+                // no branches.
+                for (int n = n_bat; n > 0; --n) {
+                    mbar_wait_a(tfull, tphase);
+                    tc_fence_after();
 #pragma unroll
-                for (int r = 0; r < B; ++r) {
-                    double w[4];
-                    lds_f64x2(w[0], w[1], slot + r * kRecSlot);
-                    lds_f64x2(w[2], w[3], slot + r * kRecSlot + 16);
-                    const uint32_t off4 = lds32(slot + r * kRecSlot + 64 - 28 * grp);
-                    const uint32_t cr = col + r * C::kCols;
-                    if (!(dbg & 1)) {
+                    for (int r = 0; r < B; ++r) {
+                        double w[4];
+                        lds_f64x2(w[0], w[1], rec + r * (int)sizeof(WinRecord));
+                        lds_f64x2(w[2], w[3], rec + r * (int)sizeof(WinRecord) + 16);
+                        const uint32_t off4 = lds32(off_addr(r));
+                        const uint32_t cr = col + r * C::kCols;
 #pragma unroll
                         for (int s2 = 0; s2 < 4; ++s2) {
                             uint32_t x[32];
@@ -479,14 +521,68 @@ k_gather_tmem(const __grid_constant__ CUtensorMap tmap, double *__restrict__ g,
                                                  acc[s2][k]);
                         }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(tfull + 32 * TS);
+                    tfull += 32; col += B * C::kCols; rec += B * (int)sizeof(WinRecord);
+                    if (++ts == TS) { ts = 0; tphase ^= 1; tfull = tm_full + 8 * q; col = col0; }
+                    if (++rs == RS) { rs = 0; rec = rec0; }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_a(tfull + 32 * TS);
-                tfull += 32; slot += 4 * kSlot; col += B * C::kCols;
-                if (++ts == TS) {
-                    ts = 0; tphase ^= 1;
-                    tfull = tm_full + 8 * q; slot = slot0; col = col0;
+            } else {
+                // One ITEM = (record of the batch, receiver of this group): one x32 TMEM load
+                // at the receiver's column shift, then 16 DFMAs.  tcgen05.ld has ~115 cycles
+                // of latency and a scheduler has only two consumer warps to hide it with, so
+                // the loop is software-pipelined: the operands of item i+1 (also across the
+                // batch hand-over, after the next stage's barrier) are requested before the
+                // DFMAs of item i run -- two receivers' operands (64 registers) in flight.
+                constexpr int kItems = 4 * B;
+                static_assert(kItems % 2 == 0, "static operand-buffer parity");
+                uint32_t xa[32], xb[32];
+                uint32_t off[B];
+                mbar_wait_a(tfull, tphase);
+                tc_fence_after();
+                off[0] = lds32(off_addr(0));
+                double w_cur = lds_f64(rec), w_nxt = 0.0;
+                tmem_ld32(xa, col - (off[0] & 0xffu));
+                for (int n = n_bat; n > 0; --n) {
+                    const uint32_t release = tfull + 32 * TS;  // tmem_empty of the stage in use
+#pragma unroll
+                    for (int it = 0; it < kItems; ++it) {
+                        uint32_t *cur = (it & 1) ? xb : xa, *nxt = (it & 1) ? xa : xb;
+                        if (it + 1 < kItems) {
+                            const int r1 = (it + 1) >> 2, s1 = (it + 1) & 3;
+                            if (s1 == 0) off[r1] = lds32(off_addr(r1));
+                            w_nxt = lds_f64(rec + r1 * (int)sizeof(WinRecord) + 8 * s1);
+                            tmem_ld32(nxt, col + r1 * C::kCols - ((off[r1] >> (8 * s1)) & 0xffu));
+                        } else {
+                            // hand-over: next TMEM stage / ring slot, request its first item
+                            tfull += 32; col += B * C::kCols; rec += B * (int)sizeof(WinRecord);
+                            if (++ts == TS) {
+                                ts = 0; tphase ^= 1; tfull = tm_full + 8 * q; col = col0;
+                            }
+                            if (++rs == RS) { rs = 0; rec = rec0; }
+                            if (n > 1) {
+                                mbar_wait_a(tfull, tphase);
+                                tc_fence_after();
+                                off[0] = lds32(off_addr(0));
+                                w_nxt = lds_f64(rec);
+                                tmem_ld32(nxt, col - (off[0] & 0xffu));
+                            }
+                        }
+                        // (ptxas gives every tcgen05.ld its own scoreboard: the DFMAs below
+                        // wait for `cur` only, not for the request just issued)
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        const int s2 = it & 3;
+#pragma unroll
+                        for (int k = 0; k < kLaneT; ++k)
+                            acc[s2][k] = fma(w_cur,
+                                             __hiloint2double((int)cur[2 * k + 1], (int)cur[2 * k]),
+                                             acc[s2][k]);
+                        w_cur = w_nxt;
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(release);
                 }
             }
             // ---- epilogue: 16 consecutive bins per receiver row ----
@@ -530,7 +626,7 @@ static EncodeTiled encode_fn() {
     return fn;
 }
 
-template <int H, int B>
+template <int H, int B, bool kPipe>
 int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRecord *recs,
            const int32_t *cta_order, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
            int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
@@ -557,28 +653,28 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
     if (!encode) return fail(-2, "cuTensorMapEncodeTiled", "driver entry point not found");
     const int64_t total = n_bands * n_alloc * n_dirs * ld;             // doubles in e_prev
     SPB_REQUIRE(total / 16 <= 2147483647LL, "histogram too large for 32-bit tensor rows");
-    CUtensorMap tmap;
-    cuuint64_t dims[2] = {16, (cuuint64_t)(total / 16)};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {16, (cuuint32_t)(32 * qpb + 2)};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)e_prev, dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled", "encode failed");
+    TmapSet tmaps;
+    for (int j = 0; j < 8; ++j) {
+        cuuint64_t dims[2] = {16, (cuuint64_t)((total - 2 * j) / 16)};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {16, (cuuint32_t)(32 * qpb + 1)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmaps.m[j], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+                            (void *)(e_prev + 2 * j), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled", "encode failed");
+    }
 
     constexpr int S = 8 / B, TS = 512 / (B * C::kCols);
-    const size_t smem = (size_t)S * (B * kBoxArea + 1024) + (size_t)TS * 4 * B * kRecSlot +
+    const size_t smem = (size_t)S * B * kBoxArea + (size_t)(S + TS) * B * sizeof(WinRecord) +
                         (2 * S + 8 * TS) * sizeof(uint64_t) + 16;
-    SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    const char *dbg_env = getenv("SPB_TMEM_DBG");          // timing experiments only
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H, B, kPipe>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)n_tiles, (unsigned)(n_bgroups * n_tchunks));
-    k_gather_tmem<H, B><<<grid, kThreads, smem, st>>>(tmap, g, ent_ptr, recs, cta_order, n_patches,
-                                                   n_alloc, n_blocks, n_dirs, b_lo, b_hi, jb_lo,
-                                                   n_jb, n_classes, t_pad, ld, pad, qpb,
-                                                   n_tchunks, dbg);
+    k_gather_tmem<H, B, kPipe><<<grid, kThreads, smem, st>>>(
+        tmaps, g, ent_ptr, recs, cta_order, n_patches, n_alloc, n_blocks, n_dirs, b_lo, b_hi,
+        jb_lo, n_jb, n_classes, t_pad, ld, pad, qpb, n_tchunks);
     return check_launch("k_gather_tmem");
 }
 
@@ -618,13 +714,21 @@ int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr
     cudaStream_t st = (cudaStream_t)stream;
     const double *ep = (const double *)e_prev;
     const tmg::WinRecord *r = (const tmg::WinRecord *)recs;
-    if (window == 4)
-        return tmg::launch<4, tmg::kBatch>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc, n_classes,
-                             n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, st);
-    if (window == 10)
-        return tmg::launch<10, tmg::kBatch>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
-                              n_classes, n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad,
-                              st);
+    const char *pipe_env = getenv("SPB_TMEM_PIPE");        // experiment switch
+    const bool pipe = pipe_env ? atoi(pipe_env) != 0 : tmg::kPipeDefault;
+#define SPB_TMEM_LAUNCH(H, P)                                                                  \
+    return tmg::launch<H, tmg::kBatch, P>(ep, (double *)g, ent_ptr, r, cta_order, n_patches,   \
+                                          n_alloc, n_classes, n_dirs, n_bands, b_lo, b_hi,     \
+                                          j_lo, j_hi, t_pad, ld, pad, st)
+    if (window == 4) {
+        if (pipe) SPB_TMEM_LAUNCH(4, true);
+        SPB_TMEM_LAUNCH(4, false);
+    }
+    if (window == 10) {
+        if (pipe) SPB_TMEM_LAUNCH(10, true);
+        SPB_TMEM_LAUNCH(10, false);
+    }
+#undef SPB_TMEM_LAUNCH
     return fail(-1, "invalid argument", "window must be 4 or 10");
 }
 

@@ -170,7 +170,7 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     if gather == "tmem" and code == _lib.F64:
         win_ptr, win_recs, win_w = build_window_records(
             sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs, n_classes, code)
-        win_ptr, win_recs = pad_record_lists(win_ptr, win_recs, tmem_batch())
+        win_ptr, win_recs = device_window_records(win_ptr, win_recs)
     else:
         ent_ptr, recs = build_tile_records(sender, receiver, ff, delay, out_dir, cls,
                                            n_patches, n_dirs, n_classes, code)
@@ -316,6 +316,17 @@ def pad_record_lists(ent_ptr, recs, multiple):
     dst = torch.arange(recs.shape[0], device=recs.device) + (new_ptr[:-1] - ent_ptr[:-1])[tile]
     out[dst] = recs
     return new_ptr.contiguous(), out
+
+
+def device_window_records(ent_ptr, recs):
+    """Window records as the kernel reads them: every tile's list padded to the pipeline
+    batch, and the shift bytes turned into TMEM column offsets -- ``2 * (delay - dbase)``, and
+    0 for an empty slot, whose weight is 0 (the consumers read the records straight from
+    shared memory, no per-record massaging on the device)."""
+    ent_ptr, recs = pad_record_lists(ent_ptr, recs, tmem_batch())
+    rel = recs[:, 64:72]
+    recs[:, 64:72] = torch.where(rel == 255, torch.zeros_like(rel), rel * 2)
+    return ent_ptr, recs
 
 
 def build_window_records(sender, receiver, ff, delay, out_dir, cls, n_patches, n_dirs,

@@ -224,8 +224,9 @@ def test_visible_pairs_scans_the_matrix_in_row_blocks():
 
 
 def decode_window_records(t):
-    """(class, receiver, src_row, delay, weight) tuples encoded in the window records
-    (csrc/exchange_tmem.cu, exchange_win.cu): {w[8] f64, rel[8] u8, src i32, dbase i32}."""
+    """(class, receiver, src_row, delay, weight) tuples encoded in the window records as the
+    kernel reads them (csrc/exchange_tmem.cu, exchange.device_window_records):
+    {w[8] f64, 2 * rel[8] u8, src i32, dbase i32}; an empty slot has w = 0 and offset 0."""
     recs, ent = t.win_recs.numpy(), t.win_ptr.numpy()
     n_blocks = -(-t.n_patches // 8)
     out, n_null = [], 0
@@ -233,18 +234,19 @@ def decode_window_records(t):
         c, jb = divmod(tile, n_blocks)
         for e in range(ent[tile], ent[tile + 1]):
             raw = recs[e]
-            w, rel = raw[:64].view(np.float64), raw[64:72]
+            w, off = raw[:64].view(np.float64), raw[64:72]
             src, dbase = raw[72:].view(np.int32)
             assert dbase % 2 == 0 and dbase >= 0
-            if np.all(rel == 255):
-                assert np.all(w == 0) and src == 0 and dbase == 0      # padding record
+            if np.all(w == 0):
+                assert np.all(off == 0) and src == 0 and dbase == 0      # padding record
                 n_null += 1
             for s in range(8):
-                if rel[s] != 255:
-                    assert rel[s] <= t.win_w and w[s] != 0
-                    out.append((c, jb * 8 + s, int(src), int(dbase) + int(rel[s]), float(w[s])))
+                if w[s] != 0:
+                    assert off[s] % 2 == 0 and off[s] // 2 <= t.win_w
+                    out.append((c, jb * 8 + s, int(src), int(dbase) + int(off[s]) // 2,
+                                float(w[s])))
                 else:
-                    assert w[s] == 0
+                    assert off[s] == 0
     return sorted(out), n_null
 
 

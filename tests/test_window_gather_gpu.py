@@ -56,8 +56,8 @@ def test_tmem_gather_equals_csr_gather(t_len, spread, width, n_bands, monkeypatc
     tables.win_ptr, tables.win_recs, tables.win_w = exchange.build_window_records(
         *(x[keep] for x in (sender, receiver, ff, delay, out_dir, cls)), n, d, c, _lib.F64,
         width=width)
-    tables.win_ptr, tables.win_recs = exchange.pad_record_lists(
-        tables.win_ptr, tables.win_recs, exchange.tmem_batch())
+    tables.win_ptr, tables.win_recs = exchange.device_window_records(
+        tables.win_ptr, tables.win_recs)
     t_pad, pad = _lib.exchange_layout(t_len, tables.max_delay, tables.dtype)
     ld = t_pad + pad
     n_alloc = n + 3                                  # padded patch axis (multi-GPU layout)

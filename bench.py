@@ -36,6 +36,11 @@ CONFIGS = {
                scattering=0.5, absorption=0.1,
                desc="C2 shoebox 5x6x4 m, 0.2 m patches (N=3700), 16 directions, 6 bands, "
                     "T=1000, K=20"),
+    "c3": dict(scene=("plane", 100.0), patch=0.5, dirs=None, bands=1, n_samples=1000, orders=0,
+               sources_grid=(4, 4, 2.0), receivers_grid=(8, 8, 1.5), scattering=1.0,
+               absorption=0.0, kind="c3",
+               desc="C3 infinite-diffuse-plane analogue: 100x100 m ground plane, 0.5 m patches "
+                    "(N=40000), 16 sources x 64 receivers, order 0, T=1000"),
     "c4": dict(scene=("canyon", 1.0), patch=1.0, dirs=None, bands=1, n_samples=2000,
                orders=50, source=(60.0, 30.0, 1.5),
                receivers=[(10.0, 30.0, 1.5), (50.0, 28.0, 1.5), (90.0, 32.0, 1.5),
@@ -71,7 +76,9 @@ def build_scene(cfg, dtype):
     from sparrowpy_b200 import pyfar_shim as pf, scenes
     kind, arg = cfg["scene"]
     walls = (scenes.shoebox(*arg) if kind == "shoebox" else
-             scenes.city_block(0, arg) if kind == "city" else scenes.street_canyon(0, arg))
+             scenes.city_block(0, arg) if kind == "city" else
+             scenes.ground_plane(-arg / 2, arg / 2, -arg / 2, arg / 2) if kind == "plane" else
+             scenes.street_canyon(0, arg))
     rad = sp.DirectionalRadiosityFast.from_polygon([sp.Polygon(*w) for w in walls],
                                                    cfg["patch"], dtype=dtype)
     nb = cfg["bands"]
@@ -88,8 +95,17 @@ def build_scene(cfg, dtype):
     air = 1e-4 * 2.0 ** np.arange(nb) if nb > 1 else np.zeros(1)
     rad.set_air_attenuation(pf.FrequencyData(air, freqs))
     rad.bake_geometry()
-    rad.init_source_energy(pf.Coordinates(*cfg["source"]))
+    if "source" in cfg:
+        rad.init_source_energy(pf.Coordinates(*cfg["source"]))
     return rad
+
+
+def grid_points(nx, ny, z, half):
+    """nx x ny points over the central part of a (2 half)^2 plane at height z."""
+    xs = (np.arange(nx) + 0.5) / nx * 1.2 * half - 0.6 * half
+    ys = (np.arange(ny) + 0.5) / ny * 1.2 * half - 0.6 * half
+    gx, gy = np.meshgrid(xs, ys, indexing="ij")
+    return np.column_stack([gx.ravel(), gy.ravel(), np.full(gx.size, float(z))])
 
 
 # ---------------------------------------------------------------------------
@@ -334,6 +350,9 @@ def main():
     if cfg.get("large"):
         run_large(args, cfg, rank, world, local_rank, max(args.warmup, 3), log)
         return
+    if cfg.get("kind") == "c3":
+        run_c3(args, cfg, rank, world, local_rank, max(args.warmup, 3), log)
+        return
 
     import torch.distributed as dist
     from sparrowpy_b200 import _lib, bake, distributed, exchange
@@ -572,6 +591,227 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c3(args, cfg, rank, world, local_rank, warmup, log):
+    """Config 3: one ground plane (coplanar patches never see each other, P = 0), many
+    sources and receivers, reflection order 0 -- the reference's infinite-diffuse-plane
+    test (tests/test_DRadiosityFast_infinite_diffuse_plane.py:59-90), where it loops over
+    receivers in Python (RadiosityFast.py:711) and allows one source (:450-451).  A step =
+    source energies of all S sources (one launch), order-0 histograms, and the mono ETC of
+    all R receivers.  Metric: (source, receiver, patch, band, bin) contributions per second,
+    S*R*N*B*T per step -- the FMAs of `_collect_receiver_energy` (RadiosityFast.py:1148-1185).
+    Receivers are sharded over the ranks (no collective in the data path)."""
+    import torch
+    import torch.distributed as dist
+    from sparrowpy_b200 import _lib, bake, exchange, pyfar_shim as pf
+
+    _lib.load()
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    t0 = time.time()
+    rad = build_scene(cfg, args.dtype)
+    torch.cuda.synchronize()
+    n = rad.n_patches
+    half = cfg["scene"][1] / 2
+    srcs = grid_points(*cfg["sources_grid"], half)
+    rcvs_all = grid_points(*cfg["receivers_grid"], half)
+    n_src, n_rcv_all = len(srcs), len(rcvs_all)
+    rcvs = rcvs_all[rank::world]
+    n_samples = cfg["n_samples"]
+    log(f"baked c3: N={n} P={rad._baked['pairs'].shape[0]} in {time.time() - t0:.1f}s; "
+        f"{n_src} sources, {len(rcvs)} of {n_rcv_all} receivers on this rank")
+    code = _lib.dtype_code(args.dtype)
+    esize = 8 if code == _lib.F64 else 4
+    tdt = _lib.torch_dtype(code)
+    g = rad._geom()
+    rad._source_energy(srcs[:1])              # installs the default BRDF / air tables
+    vi, vo, brdf, bidx = rad._brdf_tables()
+    air = torch.from_numpy(np.real(rad._air_attenuation).astype(float)).to(dev)
+    vi_d, vo_d = torch.from_numpy(vi).to(dev), torch.from_numpy(vo).to(dev)
+    brdf_d, bidx_d = torch.from_numpy(brdf).to(dev), torch.from_numpy(bidx).to(dev)
+    src_d = torch.from_numpy(srcs).to(dev)
+    rcv_d = torch.from_numpy(np.ascontiguousarray(rcvs)).to(dev)
+    n_band = int(air.shape[0])
+    empty = torch.zeros(0, dtype=torch.int64, device=dev)
+    tables = exchange.build_pair_tables(
+        empty, empty, torch.zeros(0, dtype=torch.float64, device=dev), empty, empty, empty,
+        torch.ones((1, vo.shape[1], n_band), dtype=torch.float64, device=dev), n, n_samples,
+        args.dtype)
+    ev = {k: [] for k in ("source", "init", "factors", "collect")}
+
+    def timed(key, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        ev[key].append((e0, e1))
+        return out
+
+    def step():
+        svis = bake.visibility_pt2p(src_d, g["center"], g["walls_normal"], g["walls_points"])
+        d0, e0 = timed("source", lambda: bake.source_energy_batch(
+            src_d, g["center"], g["points"], svis, air, g["wall_ids"], vi_d, brdf_d, bidx_d,
+            vo.shape[1]))
+        hist = timed("init", lambda: exchange.energy_exchange(
+            tables, e0, bake.delay_bins(d0.reshape(-1), SPEED_OF_SOUND, DT).view(n_src, n),
+            n_samples, 0))
+        rvis = bake.visibility_pt2p(rcv_d, g["center"], g["walls_normal"], g["walls_points"])
+        rt = timed("factors", lambda: bake.receiver_factors(
+            rcv_d, g["center"], g["points"], rvis, air, g["wall_ids"], vo_d, SPEED_OF_SOUND, DT,
+            n_samples))
+        return timed("collect", lambda: exchange.collect_mono(
+            hist, rt["rdir"], rt["shift"], rt["scale"]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st = torch.cuda.current_stream()
+    for _ in range(warmup):
+        step()
+    barrier()
+    for v in ev.values():
+        v.clear()
+    with ClockSampler(local_rank) as clocks:
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev_a.record(st)
+        for _ in range(args.steps):
+            mono = step()
+        ev_b.record(st)
+        barrier()
+        elapsed_ms = ev_a.elapsed_time(ev_b)
+    stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev.items()}
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    ms_per_step = elapsed_ms / args.steps
+    x_per_step = float(n_src) * n_rcv_all * n * n_band * n_samples
+    value = x_per_step / (ms_per_step * 1e-3)
+
+    # end to end through the class: host coordinates in, TimeData (host) out
+    src_c = pf.Coordinates.from_cartesian(srcs)
+    rcv_c = pf.Coordinates.from_cartesian(rcvs)
+
+    def e2e_step():
+        rad.init_source_energy_batch(src_c)
+        rad.calculate_energy_exchange(SPEED_OF_SOUND, DT, n_samples * DT, max_reflection_order=0,
+                                      recalculate=True)
+        return rad.collect_energy_receiver_mono(rcv_c).time
+
+    e2e_step()
+    barrier()
+    n_e2e = max(2, min(args.steps, 5))
+    t1 = time.perf_counter()
+    for _ in range(n_e2e):
+        etc = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t1) / n_e2e
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    same = float(np.max(np.abs(etc - mono.double().cpu().numpy())) / np.max(np.abs(etc)))
+
+    # roofline of the collection kernel: one 8-byte histogram read per contribution
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    fma = float(n_src) * len(rcvs) * n * n_band * n_samples
+    alg_bytes = fma * esize
+    compulsory = float(n_src) * n_band * n * vo.shape[1] * n_samples * esize
+    pipe = measure_fma_peak(code, dev)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_c3_rate(rad, cfg, srcs, rcvs_all, log)
+    if rank == 0:
+        c_ms = stage_ms["collect"]
+        line = {
+            "metric": "source*receiver*patch*band*bin contributions/s (order-0 ETCs at all "
+                      "receivers; BASELINE config 3)",
+            "value": value, "unit": "contributions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "gpu_launches": int(args.steps * (8 + 2 * n_src)),
+            "config": {"workload": cfg["desc"], "name": args.config, "n_patches": n,
+                       "visible_pairs": 0, "n_sources": n_src, "n_receivers": n_rcv_all,
+                       "n_directions": int(vo.shape[1]), "n_bands": n_band,
+                       "n_samples": n_samples, "reflection_orders": 0,
+                       "contributions_per_step": x_per_step,
+                       "l2": "inputs larger than L2 (order-0 histograms of all sources = "
+                             f"{compulsory / 1e9:.1f} GB)"},
+            "run": {"parallelism": f"receivers sharded x{world}" if world > 1 else "1 GPU",
+                    "stage_ms": stage_ms},
+            "clocks": clocks.summary(),
+            "roofline": {
+                "bound": "hbm", "kernel": "k_collect_partial",
+                "achieved": alg_bytes / (c_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (c_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                "avg_launch_ms": c_ms, "share_of_step": c_ms / ms_per_step,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "compulsory_bytes_per_launch": compulsory,
+                "fma_tflops": 2.0 * fma / (c_ms * 1e-3) / 1e12,
+                "fma_frac_of_measured_pipe": 2.0 * fma / (c_ms * 1e-3) / 1e12 / pipe["tflops"],
+                "fma_pipe_measured_tflops": pipe["tflops"],
+                "note": "algorithmic bytes = one histogram element per (source, receiver, "
+                        "patch, band, bin) contribution (SURVEY 8d); the rows of a band are "
+                        "shared by all receivers through L2, so frac can exceed 1 -- the "
+                        "compulsory HBM traffic is the histogram once"},
+            "e2e": {"value": x_per_step / e2e_s, "unit": "contributions/s",
+                    "h2d_bytes_per_step": int((srcs.size + rcvs.size) * 8),
+                    "d2h_bytes_per_step": int(etc.size * 8), "ms_per_step": e2e_s * 1e3,
+                    "api": "init_source_energy_batch + calculate_energy_exchange(order 0) + "
+                           "collect_energy_receiver_mono (host coordinates in, host ETCs out)"},
+            "result": {"etc_checksum": float(etc.sum()), "class_vs_operator_rel_diff": same},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_c3_rate(rad, cfg, srcs, rcvs, log, budget_s=15.0):
+    """The oracle's order-0 path (source energy, initial histogram, receiver collection:
+    universal.py:98-160, RadiosityFast.py:1037-1070, :1148-1185) for one source and a bounded
+    number of receivers, serial like the reference; extrapolated linearly to S x R."""
+    from oracle import oracle as orc
+    cen, pts, ids = rad.patches_center, rad.patches_points, rad._patch_to_wall_ids
+    wp, wn = rad._walls_points, rad._walls_normal
+    one = np.array([[[0.0, 0.0, 1.0]]])
+    brdf = np.full((1, 1, 1, 1), np.pi)
+    air = np.zeros(1)
+    t0 = time.perf_counter()
+    svis = orc.visibility_pt2p(srcs[0], cen, wn, wp)
+    e0b, d0 = orc.source_energy(srcs[0], cen, pts, svis, air)
+    e0 = orc.add_directional(e0b, srcs[0], cen, ids, one, one, brdf, np.zeros(1, np.int64))
+    etc = orc.init_energy(e0, d0, cfg["n_samples"], SPEED_OF_SOUND, DT)
+    t_src = time.perf_counter() - t0
+    n_r, t_rcv = 0, 0.0
+    while n_r < len(rcvs) and t_src + t_rcv < budget_s:
+        t0 = time.perf_counter()
+        r = rcvs[n_r]
+        v = orc.visibility_pt2p(r, cen, wn, wp)
+        f = orc.receiver_factor(r, pts, v)
+        k = orc.receiver_dir_index(cen, r, one, ids)
+        orc.collect_receiver(etc, r, cen, f, k, air, SPEED_OF_SOUND, DT)
+        t_rcv += time.perf_counter() - t0
+        n_r += 1
+    t_full = len(srcs) * (t_src + t_rcv / n_r * len(rcvs))
+    x = float(len(srcs)) * len(rcvs) * rad.n_patches * cfg["n_samples"]
+    if log:
+        log(f"cpu c3: source stage {t_src:.2f}s, {n_r} receivers {t_rcv:.2f}s")
+    return {"value": x / t_full, "unit": "contributions/s", "cores": 1, "kind": "port",
+            "seconds_per_step": t_full,
+            "sample": f"oracle order-0 path for 1 of {len(srcs)} sources and {n_r} of "
+                      f"{len(rcvs)} receivers (coplanar scene: no patch pairs), extrapolated "
+                      "linearly to all sources and receivers"}
 
 
 def run_large(args, cfg, rank, world, local_rank, warmup, log):

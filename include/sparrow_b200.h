@@ -124,10 +124,12 @@ int spb_exchange_gather_tiled(const void *e_prev, void *g, const int64_t *ent_pt
                               void *stream);
 
 /* Window records of the tensor-memory gather below (80 bytes):
- *     { double w[R]; uint8 rel[R]; int32 src; int32 dbase; }
+ *     { double w[R]; uint8 off[R]; int32 src; int32 dbase; }
  * one per (tile of R = 8 receivers, sender row, delay window [dbase, dbase + W]), dbase
- * even, rel = delay - dbase, rel = 255 for a slot without a pair; W is one of the
- * instantiated widths (4 or 10).  Tile numbering, ent_ptr, j_lo and cta_order as for
+ * even, off = 2 * (delay - dbase) = the receiver's tensor-memory column offset; a slot
+ * without a pair has w = 0 and off = 0; W is one of the instantiated widths (4 or 10).
+ * Every tile's list is padded to a multiple of spb_tmem_batch() records with null records
+ * (all zero).  Tile numbering, ent_ptr, j_lo and cta_order as for
  * spb_exchange_gather_tiled. */
 int spb_window_geometry(int dtype, int64_t *receivers_per_tile, int64_t *max_window,
                         int64_t *record_bytes);
@@ -273,6 +275,15 @@ int spb_source_energy(const double *src, const double *centers, const double *pt
                       const double *vi, int64_t n_in, const double *brdf,
                       const int64_t *brdf_index, int64_t n_out, int64_t n_bands, int64_t n,
                       double *distance, double *e0, double *energy, void *stream);
+/* The same for a batch of `n_src` sources in ONE launch (extension, SURVEY.md 8f: the
+ * reference allows one source, RadiosityFast.py:450-451): src (S,3), vis (S,N), distance (S,N),
+ * e0 (S,N,D,B), energy (S,N,B) or NULL. */
+int spb_source_energy_batch(const double *src, int64_t n_src, const double *centers,
+                            const double *pts, const uint8_t *vis, const double *air,
+                            const int64_t *patch_to_wall, const double *vi, int64_t n_in,
+                            const double *brdf, const int64_t *brdf_index, int64_t n_out,
+                            int64_t n_bands, int64_t n, double *distance, double *e0,
+                            double *energy, void *stream);
 
 /* Receiver side of `_collect_energy_patches` (RadiosityFast.py:711-748) for a batch
  * of receivers: factor[r,k] (universal.py:149-160), rdir[r,k] (:728-730), delay[r,k]

@@ -15,7 +15,7 @@ for r in rows[hi + 1:]:
     if len(r) <= mv:
         continue
     name = r[kn].split("(")[0].replace("void ", "")
-    if not name.startswith("spb::"):
+    if "::k_" not in name and not name.startswith("k_"):
         name = "(torch index/sort/fill helpers of table building)"
     agg[name][0] += 1
     agg[name][1] += float(r[mv]) / 1e6

@@ -147,6 +147,27 @@ def source_energy(source, centers, points, vis, air, patch_to_wall, vi, brdf, br
     return dist, e0, energy
 
 
+def source_energy_batch(sources, centers, points, vis, air, patch_to_wall, vi, brdf,
+                        brdf_index, n_out):
+    """:func:`source_energy` for S source positions in one launch: sources (S, 3), vis (S, N).
+    Returns (distance (S, N), e0 (S, N, D, B))."""
+    centers = _dev(centers, torch.float64)
+    dev = centers.device
+    sources = _dev(sources.reshape(-1, 3), torch.float64)
+    n_src, n, nb = sources.shape[0], centers.shape[0], air.shape[0]
+    dist = torch.empty((n_src, n), dtype=torch.float64, device=dev)
+    e0 = torch.empty((n_src, n, n_out, nb), dtype=torch.float64, device=dev)
+    for s0 in range(0, n_src, 65535):
+        s1 = min(n_src, s0 + 65535)
+        _lib.call("spb_source_energy_batch", sources[s0:s1], s1 - s0, centers,
+                  _dev(points, torch.float64), _dev(vis[s0:s1], torch.uint8),
+                  _dev(air, torch.float64), _dev(patch_to_wall, torch.int64),
+                  _dev(vi, torch.float64), vi.shape[1], _dev(brdf, torch.float64),
+                  _dev(brdf_index, torch.int64), n_out, nb, n, dist[s0:s1], e0[s0:s1], None,
+                  _lib.stream_ptr())
+    return dist, e0
+
+
 def receiver_factors(receivers, centers, points, vis, air, patch_to_wall, vo,
                      speed_of_sound, dt, n_samples):
     """Receiver side of ``_collect_energy_patches`` (RadiosityFast.py:711-748) for a

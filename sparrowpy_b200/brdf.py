@@ -52,7 +52,9 @@ def create_from_scattering(source_directions, receiver_directions,
         absorption = np.real(np.asarray(absorption_coefficient.freq)).flatten()
     n_bins = len(freqs)
     brdf = np.zeros((source_directions.csize, receiver_directions.csize, n_bins))
-    receiver_weights = np.asarray(receiver_directions.weights, float).copy()
+    # in place, as in the reference (brdf.py:103-104): the caller's weights come back
+    # normalised to the hemisphere (sum = 2 pi)
+    receiver_weights = receiver_directions.weights
     receiver_weights *= 2 * np.pi / np.sum(receiver_weights)
     scattering = np.real(np.asarray(scattering_coefficient.freq)).flatten()
     image_source = source_directions.copy()
@@ -95,7 +97,7 @@ def create_from_directional_scattering(source_directions, receiver_directions,
         absorption = np.real(np.asarray(absorption_coefficient.freq)).flatten()
     cos_receiver = np.cos(np.asarray(receiver_directions.colatitude))[
         np.newaxis, :, np.newaxis]
-    receiver_weights = np.asarray(receiver_directions.weights, float).copy()
+    receiver_weights = receiver_directions.weights        # in place (brdf.py:205-206)
     receiver_weights *= 2 * np.pi / np.sum(receiver_weights)
     brdf = np.real(np.asarray(directional_scattering.freq)) / receiver_weights[
         ..., np.newaxis] / cos_receiver

@@ -521,6 +521,13 @@ k_source_energy(const double *__restrict__ src, const double *__restrict__ cente
                 double *__restrict__ energy) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
+    // blockIdx.y = source of a batch: all per-source arrays are stacked along the first axis
+    const int64_t is = blockIdx.y;
+    src += 3 * is;
+    vis += is * n;
+    distance += is * n;
+    e0 += is * n * n_out * n_bands;
+    if (energy) energy += is * n * n_bands;
     const double s[3] = {src[0], src[1], src[2]};
     double c[3], patch[12];
     for (int k = 0; k < 3; ++k) c[k] = centers[3 * j + k];
@@ -767,6 +774,23 @@ int spb_source_energy(const double *src, const double *centers, const double *pt
                 brdf_index && distance && e0, "null pointer");
     if (n == 0) return 0;
     k_source_energy<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        src, centers, pts, vis, air, patch_to_wall, vi, n_in, brdf, brdf_index, n_out, n_bands,
+        n, distance, e0, energy);
+    return check_launch("k_source_energy");
+}
+
+int spb_source_energy_batch(const double *src, int64_t n_src, const double *centers,
+                            const double *pts, const uint8_t *vis, const double *air,
+                            const int64_t *patch_to_wall, const double *vi, int64_t n_in,
+                            const double *brdf, const int64_t *brdf_index, int64_t n_out,
+                            int64_t n_bands, int64_t n, double *distance, double *e0,
+                            double *energy, void *stream) {
+    SPB_REQUIRE(src && centers && pts && vis && air && patch_to_wall && vi && brdf &&
+                brdf_index && distance && e0, "null pointer");
+    SPB_REQUIRE(n_src >= 0 && n_src <= 65535, "at most 65535 sources per call");
+    if (n == 0 || n_src == 0) return 0;
+    dim3 grid((unsigned)ceil_div(n, 128), (unsigned)n_src);
+    k_source_energy<<<grid, 128, 0, (cudaStream_t)stream>>>(
         src, centers, pts, vis, air, patch_to_wall, vi, n_in, brdf, brdf_index, n_out, n_bands,
         n, distance, e0, energy);
     return check_launch("k_source_energy");

@@ -191,8 +191,12 @@ k_collect_partial(const T *__restrict__ e_total, const int32_t *__restrict__ rdi
                   int64_t n_patches, int64_t n_alloc, int64_t n_dirs, int64_t n_bands,
                   int64_t n_samples, int64_t ld, int64_t pad, T *__restrict__ partial,
                   int64_t n_split) {
-    const int64_t rb = blockIdx.y;             // receiver * B + band
-    const int64_t r = rb / n_bands, b = rb % n_bands;
+    // blockIdx.y = band * R + receiver: CTAs that are launched together read the same rows
+    // of the same band for different receivers, so the histogram is streamed from HBM once
+    // per (band, split) and the other receivers hit in L2
+    const int64_t n_rcv = gridDim.y / n_bands;
+    const int64_t b = blockIdx.y / n_rcv, r = blockIdx.y - b * n_rcv;
+    const int64_t rb = r * n_bands + b;        // output row: receiver * B + band
     const int64_t split = blockIdx.z;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // output bin
     const int64_t k_lo = n_patches * split / n_split;

@@ -21,20 +21,33 @@
 // operands with two tcgen05.ld.32x32b.x16 at column 2 (H - rel).
 //
 // Pipeline per record (one (tile, sender row, delay window), 80 bytes, the records of
-// exchange.build_window_records):
-//   producer warp : one 2-D TMA tensor load (rows of 16 doubles, SWIZZLE_128B) of the
-//                   sender window + a bulk copy of the record into a shared-memory stage
+// exchange.build_window_records in the device encoding of exchange.device_window_records):
+//   4 producer warps: (one per shared-memory stage, one working lane each) one 2-D TMA tensor
+//                   load per band (rows of 16 doubles, SWIZZLE_128B) of the sender window,
+//                   through the one of 8 phase-shifted tensor maps that makes the window
+//                   start on a 16-byte chunk boundary of its row, + a bulk copy of the batch's
+//                   records into a shared-memory ring that the consumers read directly
 //   4 fill warps  : (one per TMEM lane quarter) read the lane's row from the swizzled
 //                   stage with conflict-free LDS.128 (the swizzle makes the 128-byte lane
-//                   pitch hit 8 different bank groups) and write it with tcgen05.st into a
-//                   ring of TMEM stages; they also hand the weights to the consumers
+//                   pitch hit 8 different bank groups) at static addresses and write it with
+//                   tcgen05.st into a ring of TMEM stages
 //   8 consumer warps: (quarter q, receiver group g) 16 bins x 4 receivers per thread =
 //                   64 FP64 accumulators; per receiver 2 tcgen05.ld + 16 DFMA.
 // Quarters run decoupled (per-quarter mbarriers).  Registers are re-balanced with
-// setmaxnreg (consumers 184, fill 104, producer 40).
+// setmaxnreg (consumers 184, fill 104, producers 40).
 //
 // When the histogram is shorter than 2048 bins the four lane quarters are spread over
 // several bands instead (same records, other energy rows), so no lane idles.
+//
+// Measured on B200, C4 (6.17 M records, 8.3 x 10^10 useful FMAs per launch), SPB_TMEM_DBG
+// experiments: data movement + hand-overs alone 9.1 ms (103 GB from L2 = 11.3 TB/s, the
+// chip's L2 throughput cap), + fill 10.5 ms, + consumers without fill 11.6 ms, everything
+// 13.4 ms = 44 % of the measured FP64 FMA peak.  History: one producer warp 15.1 ms (its
+// serial issue chain of ~1300 cycles per batch was the bound), per-record hand-overs 18.9 ms;
+// a software-pipelined consumer loop (operands of the next receiver requested before the
+// DFMAs of the current one, 208-216 consumer registers, fill warps at 56-72) measured
+// 13.4-13.7 ms -- no gain, because the L2 -> SM window traffic, not the TMEM latency, is what
+// the consumers wait for -- and was removed.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -48,7 +61,6 @@ constexpr int kLaneT = 16;                     // consecutive time bins per TMEM
 constexpr int kQuarterT = 32 * kLaneT;         // 512 bins per lane quarter
 constexpr int kBoxArea = 20480;                // bytes reserved for the staged boxes of a record
 constexpr int kBatch = 2;                      // records per pipeline hand-over
-constexpr bool kPipeDefault = false;           // software-pipelined consumer loop
 constexpr int kThreads = 512;   // 8 consumer + 4 fill + 4 producer warps; 512 x 128 regs
                                 // at launch = the whole file, so setmaxnreg only re-deals it
 
@@ -117,19 +129,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t *r, uint32_t addr) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
           "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
           "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(addr));
-}
-// 32 consecutive columns = the 16 doubles a lane needs for one receiver
-__device__ __forceinline__ void tmem_ld32(uint32_t *r, uint32_t addr) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
-        "%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
-          "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-          "=r"(r[31])
         : "r"(addr));
 }
 __device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t *r) {
@@ -216,11 +215,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void lds_f64x2(double &a, double &b, uint32_t addr) {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -239,32 +233,19 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) {
 // stage into the TMEM stage.  The producer picks, per record, the tensor map whose origin
 // makes the lane's row start at chunk 0 of its tensor row, so the chunk addresses are
 // static: p0 / p1 = address of the lane's tensor row / the next one with the row's swizzle
-// key folded in (logical chunk cc of a row is at p ^ (cc << 4)).
-// kPasses = 1: the whole row through the registers at once (one shared-memory latency per
-// record); 2: at most 8 chunks at a time (for a fill warp that runs on 56 registers).
-template <int H, int kPasses>
+// key folded in (logical chunk cc of a row is at p ^ (cc << 4)).  The whole row goes through
+// the registers at once: all LDS.128 are independent (one shared-memory latency per
+// record), then the fewest power-of-two tcgen05.st.
+template <int H>
 __device__ __forceinline__ void fill_row(uint32_t p0, uint32_t p1, uint32_t taddr) {
     using C = Cfg<H>;
-    constexpr int kFirst = kPasses == 1 ? C::kChunks : (C::kChunks < 8 ? C::kChunks : 8);
-    {
-        uint32_t v[4 * kFirst];
+    uint32_t v[C::kCols];
 #pragma unroll
-        for (int i = 0; i < kFirst; ++i) {
-            const uint4 x = lds128(i < 8 ? p0 ^ (uint32_t)(i << 4) : p1 ^ (uint32_t)((i - 8) << 4));
-            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-        }
-        tmem_store_row<4 * kFirst>(taddr, v);
+    for (int i = 0; i < C::kChunks; ++i) {
+        const uint4 x = lds128(i < 8 ? p0 ^ (uint32_t)(i << 4) : p1 ^ (uint32_t)((i - 8) << 4));
+        v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
     }
-    if constexpr (C::kChunks > kFirst) {
-        constexpr int kRest = C::kChunks - kFirst;
-        uint32_t v[4 * kRest];
-#pragma unroll
-        for (int i = 0; i < kRest; ++i) {
-            const uint4 x = lds128(p1 ^ (uint32_t)((i + kFirst - 8) << 4));
-            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-        }
-        tmem_store_row<4 * kRest>(taddr + 4 * kFirst, v);
-    }
+    tmem_store_row<C::kCols>(taddr, v);
 }
 
 // Tensor maps of the previous-order histogram seen as rows of 16 doubles, one per starting
@@ -275,31 +256,30 @@ struct TmapSet {
 };
 
 // Register deal per role (setmaxnreg); launch = 16 warps x 128.
-template <bool kPipe>
 struct Regs {
-    static constexpr int kConsumer = kPipe ? 216 : 184;
-    static constexpr int kFill = kPipe ? 56 : 104;
-    static constexpr int kProducer = kPipe ? 24 : 40;
+    static constexpr int kConsumer = 184;
+    static constexpr int kFill = 104;
+    static constexpr int kProducer = 40;
     // setmaxnreg.inc can only take what setmaxnreg.dec released inside the CTA (a pool that
     // starts empty): the re-deal must not need more registers than the launch allocated
     static_assert(8 * kConsumer + 4 * kFill + 4 * kProducer <= 16 * 128,
                   "register re-deal exceeds the launch allocation (the kernel would hang)");
 };
 
-template <int H, int B, bool kPipe>
+template <int H, int B>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
               const int64_t *__restrict__ ent_ptr, const WinRecord *__restrict__ recs,
               const int32_t *__restrict__ cta_order, int64_t n_patches, int64_t n_alloc,
               int64_t n_blocks, int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t jb_lo,
               int64_t n_jb, int64_t n_classes, int64_t t_pad, int64_t ld, int64_t pad, int qpb,
-              int n_tchunks) {
+              int n_tchunks, int dbg) {
     // Every hand-over of the pipeline (producer -> fill -> consumers) moves a BATCH of B
     // records: the barrier waits, fences and arrivals are a serial chain of a few hundred
     // cycles per hand-over in every role, and per single record that chain, not any
     // bandwidth, bounded the kernel (measured: 480 clk per record with no data moved at all).
     using C = Cfg<H>;
-    using R = Regs<kPipe>;
+    using R = Regs;
     constexpr int S = 8 / B;                           // shared-memory stages (of B records)
     constexpr int TS = 512 / (B * C::kCols);           // TMEM stages (of B rows per lane)
     // The records themselves go into a ring of S + TS batches that the consumers read
@@ -453,9 +433,10 @@ k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
                 mbar_wait_a(sfull, sphase);
                 mbar_wait_a(tfull + 32 * TS, tphase);
                 tc_fence_after();
+                if (!(dbg & 2))
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    fill_row<H, kPipe ? 2 : 1>(st + r * kBoxArea + off0, st + r * kBoxArea + off1,
+                    fill_row<H>(st + r * kBoxArea + off0, st + r * kBoxArea + off1,
                                                tcol + r * C::kCols);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
@@ -491,7 +472,7 @@ k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
             // address of the 4 offset bytes of record r: base of the record + 64 + 4 grp
             // = (rec + r * 80) - 32 grp + 64 + 4 grp
             auto off_addr = [&](int r) { return rec + r * (int)sizeof(WinRecord) + 64 - 28 * grp; };
-            if constexpr (!kPipe) {
+            {
                 // Per receiver: one x32 load, 16 DFMAs; ptxas overlaps the next receiver's
                 // load with the DFMAs as far as the registers allow, and the two consumer
                 // warps of a scheduler overlap each other's TMEM latency.  Empty slots have
@@ -507,6 +488,7 @@ k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
                         lds_f64x2(w[2], w[3], rec + r * (int)sizeof(WinRecord) + 16);
                         const uint32_t off4 = lds32(off_addr(r));
                         const uint32_t cr = col + r * C::kCols;
+                        if (!(dbg & 1))
 #pragma unroll
                         for (int s2 = 0; s2 < 4; ++s2) {
                             uint32_t x[32];
@@ -527,62 +509,6 @@ k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
                     tfull += 32; col += B * C::kCols; rec += B * (int)sizeof(WinRecord);
                     if (++ts == TS) { ts = 0; tphase ^= 1; tfull = tm_full + 8 * q; col = col0; }
                     if (++rs == RS) { rs = 0; rec = rec0; }
-                }
-            } else {
-                // One ITEM = (record of the batch, receiver of this group): one x32 TMEM load
-                // at the receiver's column shift, then 16 DFMAs.  tcgen05.ld has ~115 cycles
-                // of latency and a scheduler has only two consumer warps to hide it with, so
-                // the loop is software-pipelined: the operands of item i+1 (also across the
-                // batch hand-over, after the next stage's barrier) are requested before the
-                // DFMAs of item i run -- two receivers' operands (64 registers) in flight.
-                constexpr int kItems = 4 * B;
-                static_assert(kItems % 2 == 0, "static operand-buffer parity");
-                uint32_t xa[32], xb[32];
-                uint32_t off[B];
-                mbar_wait_a(tfull, tphase);
-                tc_fence_after();
-                off[0] = lds32(off_addr(0));
-                double w_cur = lds_f64(rec), w_nxt = 0.0;
-                tmem_ld32(xa, col - (off[0] & 0xffu));
-                for (int n = n_bat; n > 0; --n) {
-                    const uint32_t release = tfull + 32 * TS;  // tmem_empty of the stage in use
-#pragma unroll
-                    for (int it = 0; it < kItems; ++it) {
-                        uint32_t *cur = (it & 1) ? xb : xa, *nxt = (it & 1) ? xa : xb;
-                        if (it + 1 < kItems) {
-                            const int r1 = (it + 1) >> 2, s1 = (it + 1) & 3;
-                            if (s1 == 0) off[r1] = lds32(off_addr(r1));
-                            w_nxt = lds_f64(rec + r1 * (int)sizeof(WinRecord) + 8 * s1);
-                            tmem_ld32(nxt, col + r1 * C::kCols - ((off[r1] >> (8 * s1)) & 0xffu));
-                        } else {
-                            // hand-over: next TMEM stage / ring slot, request its first item
-                            tfull += 32; col += B * C::kCols; rec += B * (int)sizeof(WinRecord);
-                            if (++ts == TS) {
-                                ts = 0; tphase ^= 1; tfull = tm_full + 8 * q; col = col0;
-                            }
-                            if (++rs == RS) { rs = 0; rec = rec0; }
-                            if (n > 1) {
-                                mbar_wait_a(tfull, tphase);
-                                tc_fence_after();
-                                off[0] = lds32(off_addr(0));
-                                w_nxt = lds_f64(rec);
-                                tmem_ld32(nxt, col - (off[0] & 0xffu));
-                            }
-                        }
-                        // (ptxas gives every tcgen05.ld its own scoreboard: the DFMAs below
-                        // wait for `cur` only, not for the request just issued)
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        const int s2 = it & 3;
-#pragma unroll
-                        for (int k = 0; k < kLaneT; ++k)
-                            acc[s2][k] = fma(w_cur,
-                                             __hiloint2double((int)cur[2 * k + 1], (int)cur[2 * k]),
-                                             acc[s2][k]);
-                        w_cur = w_nxt;
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_a(release);
                 }
             }
             // ---- epilogue: 16 consecutive bins per receiver row ----
@@ -626,7 +552,7 @@ static EncodeTiled encode_fn() {
     return fn;
 }
 
-template <int H, int B, bool kPipe>
+template <int H, int B>
 int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRecord *recs,
            const int32_t *cta_order, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
            int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
@@ -669,12 +595,14 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
     constexpr int S = 8 / B, TS = 512 / (B * C::kCols);
     const size_t smem = (size_t)S * B * kBoxArea + (size_t)(S + TS) * B * sizeof(WinRecord) +
                         (2 * S + 8 * TS) * sizeof(uint64_t) + 16;
-    SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H, B, kPipe>,
+    SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H, B>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char *dbg_env = getenv("SPB_TMEM_DBG");   // timing experiments: 1 = consumers idle,
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;    // 2 = fill idle (results are wrong)
     dim3 grid((unsigned)n_tiles, (unsigned)(n_bgroups * n_tchunks));
-    k_gather_tmem<H, B, kPipe><<<grid, kThreads, smem, st>>>(
+    k_gather_tmem<H, B><<<grid, kThreads, smem, st>>>(
         tmaps, g, ent_ptr, recs, cta_order, n_patches, n_alloc, n_blocks, n_dirs, b_lo, b_hi,
-        jb_lo, n_jb, n_classes, t_pad, ld, pad, qpb, n_tchunks);
+        jb_lo, n_jb, n_classes, t_pad, ld, pad, qpb, n_tchunks, dbg);
     return check_launch("k_gather_tmem");
 }
 
@@ -714,21 +642,14 @@ int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr
     cudaStream_t st = (cudaStream_t)stream;
     const double *ep = (const double *)e_prev;
     const tmg::WinRecord *r = (const tmg::WinRecord *)recs;
-    const char *pipe_env = getenv("SPB_TMEM_PIPE");        // experiment switch
-    const bool pipe = pipe_env ? atoi(pipe_env) != 0 : tmg::kPipeDefault;
-#define SPB_TMEM_LAUNCH(H, P)                                                                  \
-    return tmg::launch<H, tmg::kBatch, P>(ep, (double *)g, ent_ptr, r, cta_order, n_patches,   \
-                                          n_alloc, n_classes, n_dirs, n_bands, b_lo, b_hi,     \
-                                          j_lo, j_hi, t_pad, ld, pad, st)
-    if (window == 4) {
-        if (pipe) SPB_TMEM_LAUNCH(4, true);
-        SPB_TMEM_LAUNCH(4, false);
-    }
-    if (window == 10) {
-        if (pipe) SPB_TMEM_LAUNCH(10, true);
-        SPB_TMEM_LAUNCH(10, false);
-    }
-#undef SPB_TMEM_LAUNCH
+    if (window == 4)
+        return tmg::launch<4, tmg::kBatch>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
+                                           n_classes, n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad,
+                                           ld, pad, st);
+    if (window == 10)
+        return tmg::launch<10, tmg::kBatch>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
+                                            n_classes, n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad,
+                                            ld, pad, st);
     return fail(-1, "invalid argument", "window must be 4 or 10");
 }
 

@@ -158,13 +158,60 @@ class TimeData:
         return self.time.shape[:-1]
 
 
+def _view_up_matrix(view, up):
+    """Matrix that ``pf.Orientations.from_view_up`` hands to scipy's ``Rotation.from_matrix``
+    (pyfar, unpinned in the reference's pyproject.toml:32; classes/orientations.py): rows
+    are view, up and right = view x up."""
+    view, up = np.asarray(view, float), np.asarray(up, float)
+    if not np.linalg.norm(view) or not np.linalg.norm(up):
+        raise ValueError("View and Up Vectors must have a length.")
+    if not np.isclose(0.0, float(np.dot(view, up))):
+        raise ValueError("View and Up vectors must be perpendicular.")
+    return np.stack([view, up, np.cross(view, up)])
+
+
+def wall_rotation_euler(wall_normal, wall_up):
+    """The 'xyz' Euler angles (degrees) that ``_rotate_coords_to_normal`` (reference
+    RadiosityFast.py:971-986) derives for a wall:
+    ``(from_view_up(normal, up).inv() * from_view_up([0,0,1], [1,0,0])).as_euler('xyz', True)``
+    -- the same scipy calls pyfar's Orientations (a scipy Rotation subclass) makes."""
+    import warnings
+    from scipy.spatial.transform import Rotation
+    o1 = Rotation.from_matrix(_view_up_matrix(wall_normal, wall_up))
+    o2 = Rotation.from_matrix(_view_up_matrix([0.0, 0.0, 1.0], [1.0, 0.0, 0.0]))
+    with warnings.catch_warnings():             # gimbal lock: scipy picks the third angle = 0
+        warnings.simplefilter("ignore", UserWarning)
+        return (o1.inv() * o2).as_euler('xyz', True).flatten()
+
+
+def rotate_to_wall(coords, wall_normal, wall_up):
+    """``coords.copy(); .rotate('xyz', euler); .radius = 1`` of the reference
+    (RadiosityFast.py:979-985) without pyfar: scipy applies the rotation, the radius is set
+    through pyfar's spherical round trip (``cart2sph`` / ``sph2cart`` of
+    classes/coordinates.py, which also flushes components below machine epsilon to zero)."""
+    from scipy.spatial.transform import Rotation
+    rot = Rotation.from_euler('xyz', wall_rotation_euler(wall_normal, wall_up), degrees=True)
+    shape = coords.cshape
+    pts = rot.apply(np.asarray(coords.cartesian, float).reshape(-1, 3))
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    radius = np.sqrt(x ** 2 + y ** 2 + z ** 2)
+    z_div_r = np.divide(z, radius, out=np.zeros_like(radius), where=radius != 0)
+    colatitude = np.arccos(z_div_r)
+    azimuth = np.mod(np.arctan2(y, x), 2 * np.pi)
+    r_sin_cola = 1.0 * np.sin(colatitude)
+    out = np.stack([r_sin_cola * np.cos(azimuth), r_sin_cola * np.sin(azimuth),
+                    1.0 * np.cos(colatitude)], axis=-1)
+    out[np.abs(out) < np.finfo(float).eps] = 0
+    res = Coordinates.from_cartesian(out.reshape(shape + (3,)),
+                                     weights=getattr(coords, "weights", None))
+    return res
+
+
 def rotation_to_wall_frame(wall_normal, wall_up):
     """Rotation taking the BRDF frame (normal +z, up +x) to a wall's frame.
 
-    Stands in for ``pf.Orientations.from_view_up(...)``-based
-    ``_rotate_coords_to_normal`` (reference RadiosityFast.py:971-986).  pyfar is
-    absent, so this rotation is NOT pinned against the reference ("parity
-    unpinned" for this helper; the kernels take already-rotated directions).
+    The closed form of what :func:`rotate_to_wall` applies (columns = images of the
+    BRDF-frame axes x (up), y, z (normal)); kept for tests and for building scenes.
     """
     n = np.asarray(wall_normal, float)
     n = n / np.linalg.norm(n)

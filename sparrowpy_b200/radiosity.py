@@ -341,14 +341,10 @@ class DirectionalRadiosityFast:
         air = torch.from_numpy(np.real(self._air_attenuation).astype(float)).to(dev)
         vi_d, brdf_d = torch.from_numpy(vi).to(dev), torch.from_numpy(brdf).to(dev)
         bidx_d = torch.from_numpy(bidx).to(dev)
-        d0s, e0s = [], []
-        for s in range(src.shape[0]):
-            d0, e0, _ = bake.source_energy(
-                src[s], g["center"], g["points"], svis[s], air, g["wall_ids"], vi_d, brdf_d,
-                bidx_d, vo.shape[1])
-            d0s.append(d0)
-            e0s.append(e0)
-        return svis, torch.stack(d0s), torch.stack(e0s)
+        d0, e0 = bake.source_energy_batch(
+            src, g["center"], g["points"], svis, air, g["wall_ids"], vi_d, brdf_d, bidx_d,
+            vo.shape[1])
+        return svis, d0, e0
 
     # ------------------------------------------------------------------
     # exchange: RadiosityFast.py:524-568
@@ -798,16 +794,10 @@ class DirectionalRadiosityFast:
 
 def _rotate_coords_to_normal(wall_normal, wall_up_vector, sources, receivers):
     """Rotate BRDF directions (frame: normal +z, up +x) into a wall's frame
-    (RadiosityFast.py:971-986; the pyfar-based original is not available here, see
-    pyfar_shim.rotation_to_wall_frame)."""
-    rot = pyfar_shim.rotation_to_wall_frame(wall_normal, wall_up_vector)
-    out = []
-    for c in (sources, receivers):
-        xyz = np.asarray(c.cartesian, float).reshape(-1, 3) @ rot.T
-        xyz = xyz / np.sqrt(np.sum(xyz ** 2, axis=-1, keepdims=True))
-        weights = getattr(c, "weights", None)
-        out.append(pyfar_shim.Coordinates.from_cartesian(xyz, weights=weights))
-    return out[0], out[1]
+    (RadiosityFast.py:971-986): the reference's pyfar calls restated on scipy's Rotation,
+    see pyfar_shim.rotate_to_wall."""
+    return (pyfar_shim.rotate_to_wall(sources, wall_normal, wall_up_vector),
+            pyfar_shim.rotate_to_wall(receivers, wall_normal, wall_up_vector))
 
 
 def _object_array(items):

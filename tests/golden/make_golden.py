@@ -10,7 +10,8 @@ fixtures next to this script.  The only thing supplied from outside the referenc
 is a stand-in for the absent pyfar package (``sparrowpy_b200.pyfar_shim``) and,
 because ``pf.Orientations`` is part of that absent package, the per-wall BRDF
 direction rotation (``_rotate_coords_to_normal``, reference
-RadiosityFast.py:971-986): the rotated direction arrays are therefore *inputs* of
+RadiosityFast.py:971-986), restated on the scipy ``Rotation`` calls that pyfar makes
+(``pyfar_shim.rotate_to_wall``): the rotated direction arrays are therefore *inputs* of
 the fixtures, not pinned outputs.
 
 The fixtures pin (a) the CPU oracle in ``oracle/`` and (b) the CUDA path.
@@ -38,14 +39,9 @@ import numba  # noqa: E402
 
 
 def _rotate_coords_to_normal(wall_normal, wall_up_vector, sources, receivers):
-    rot = pyfar_shim.rotation_to_wall_frame(wall_normal, wall_up_vector)
-    out = []
-    for c in (sources, receivers):
-        cp = c.copy()
-        cp.apply_matrix(rot)
-        cp.radius = 1
-        out.append(cp)
-    return out[0], out[1]
+    # the reference's pyfar calls restated on scipy's Rotation (pyfar is absent here)
+    return (pyfar_shim.rotate_to_wall(sources, wall_normal, wall_up_vector),
+            pyfar_shim.rotate_to_wall(receivers, wall_normal, wall_up_vector))
 
 
 RF._rotate_coords_to_normal = _rotate_coords_to_normal
@@ -414,6 +410,83 @@ def gen_directivity_metrics():
          elevation_deg=el)
 
 
+def gen_brdf_builders():
+    """The reference's BRDF builders (sparrowpy/brdf.py:8-224) driven with the pyfar
+    stand-in: direction sets with unnormalised weights, several bands, with and without
+    absorption.  Pins sparrowpy_b200/brdf.py."""
+    from sparrowpy import brdf as ref_brdf
+    rng = np.random.default_rng(7)
+    out = {}
+    for tag, (n_az, cols) in {"a": (4, (45.0,)), "b": (8, (30.0, 60.0)),
+                              "c": (6, (20.0, 50.0, 75.0))}.items():
+        dirs, w = scenes.hemisphere_directions(n_az, cols)
+        w = w * rng.uniform(0.5, 2.0)                       # weights need not be normalised
+        freqs = np.array([125.0, 500.0, 2000.0])
+        s = rng.uniform(0.05, 0.95, 3)
+        alpha = rng.uniform(0.0, 0.6, 3)
+        src = pyfar_shim.Coordinates.from_cartesian(dirs, weights=w.copy())
+        rcv = pyfar_shim.Coordinates.from_cartesian(dirs, weights=w.copy())
+        b1 = ref_brdf.create_from_scattering(
+            src, rcv, pyfar_shim.FrequencyData(s, freqs), pyfar_shim.FrequencyData(alpha, freqs))
+        rcv2 = pyfar_shim.Coordinates.from_cartesian(dirs, weights=w.copy())
+        b2 = ref_brdf.create_from_scattering(src, rcv2, pyfar_shim.FrequencyData(s, freqs))
+        sd = rng.uniform(0.0, 1.0, (len(dirs), len(dirs), 3))
+        sd /= sd.sum(axis=1, keepdims=True)
+        rcv3 = pyfar_shim.Coordinates.from_cartesian(dirs, weights=w.copy())
+        b3 = ref_brdf.create_from_directional_scattering(
+            src, rcv3, pyfar_shim.FrequencyData(sd, freqs),
+            pyfar_shim.FrequencyData(alpha, freqs))
+        out.update({f"{tag}_dirs": dirs, f"{tag}_weights": w, f"{tag}_freqs": freqs,
+                    f"{tag}_scattering": s, f"{tag}_absorption": alpha,
+                    f"{tag}_directional": sd,
+                    f"{tag}_brdf_scattering": np.real(b1.freq),
+                    f"{tag}_brdf_scattering_noabs": np.real(b2.freq),
+                    f"{tag}_brdf_directional": np.real(b3.freq),
+                    f"{tag}_weights_after": np.asarray(rcv.weights)})
+    save("brdf_builders", **out)
+
+
+def gen_direct_sound():
+    """``calculate_direct_sound`` (RadiosityFast.py:605-657) of the reference class, called
+    unbound on a minimal stand-in object (it only reads the attributes set below)."""
+    import types
+    rng = np.random.default_rng(11)
+    src = np.array([1.3, -0.4, 1.7])
+    rcv = rng.uniform(-6, 6, (12, 3))
+    air = np.array([0.0, 1e-3, 7e-3])
+    c, dt = 343.2, 0.5e-3
+    obj = types.SimpleNamespace(
+        _source=pyfar_shim.Coordinates(*src), n_bins=3, _air_attenuation=air,
+        speed_of_sound=c, _etc_time_resolution=dt, _frequencies=np.array([250., 1e3, 4e3]))
+    direct, delay = RF.DirectionalRadiosityFast.calculate_direct_sound(
+        obj, pyfar_shim.Coordinates.from_cartesian(rcv))
+    save("direct_sound", source=src, receivers=rcv, air_attenuation=air, speed_of_sound=c,
+         dt=dt, direct_sound=direct, n_sample_delay=delay)
+
+
+def gen_wall_rotation():
+    """Invariants of ``_rotate_coords_to_normal`` that the reference's tests state
+    (tests/test_DRadiosityFast.py:46-107, :153-172) evaluated on the restated rotation, plus
+    the rotated direction sets themselves (regression vectors for the shim)."""
+    d, w = scenes.hemisphere_directions(8, (30.0, 60.0))
+    coords = pyfar_shim.Coordinates.from_cartesian(d, weights=w)
+    frames = [([1, 0, 0], [0, 0, 1]), ([0, 1, 0], [0, 0, -1]), ([0, 0, 1], [1, 0, 0]),
+              ([0, 0, -1], [0, 1, 0]), ([-1, 0, 0], [0, 1, 0]), ([0, -1, 0], [1, 0, 0])]
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        n = rng.normal(size=3)
+        n /= np.linalg.norm(n)
+        u = rng.normal(size=3)
+        u -= np.dot(u, n) * n
+        u /= np.linalg.norm(u)
+        frames.append((n, u))
+    normals = np.array([f[0] for f in frames], float)
+    ups = np.array([f[1] for f in frames], float)
+    rotated = np.array([_rotate_coords_to_normal(n, u, coords, coords)[0].cartesian
+                        for n, u in zip(normals, ups)])
+    save("wall_rotation", dirs=d, weights=w, normals=normals, ups=ups, rotated=rotated)
+
+
 def main():
     only = set(sys.argv[1:])
 
@@ -432,6 +505,12 @@ def main():
         print("point-patch"); gen_point_patch()
     if want("directivity"):
         print("directivity metrics"); gen_directivity_metrics()
+    if want("brdf"):
+        print("brdf builders"); gen_brdf_builders()
+    if want("direct"):
+        print("direct sound"); gen_direct_sound()
+    if want("rotation"):
+        print("wall rotation"); gen_wall_rotation()
 
     if want("cube"):
         print("scene cube05 (reference tests/test_DRadiosityFast.py:19-29)")

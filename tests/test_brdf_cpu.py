@@ -88,3 +88,31 @@ def test_builder_output_feeds_set_wall_brdf():
                                        pf.FrequencyData([0.1, 0.2], [500, 1000]))
     rad.set_wall_brdf(np.arange(6), data, c, c)
     assert rad.n_bins == 2 and rad._brdf[0].shape == (8, 8, 2)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_builders_match_the_live_reference(tag):
+    """Vectors produced by the reference's own sparrowpy/brdf.py (driven with the pyfar
+    stand-in, tests/golden/make_golden.py::gen_brdf_builders): both builders to 1e-14, and
+    the reference's side effect on the receiver weights (normalised in place to 2 pi,
+    brdf.py:103-104)."""
+    from conftest import load_golden
+    from sparrowpy_b200 import brdf, pyfar_shim as pf
+    g = load_golden("brdf_builders")
+    dirs, w, freqs = g[f"{tag}_dirs"], g[f"{tag}_weights"], g[f"{tag}_freqs"]
+    s, alpha = g[f"{tag}_scattering"], g[f"{tag}_absorption"]
+    src = pf.Coordinates.from_cartesian(dirs, weights=w.copy())
+    rcv = pf.Coordinates.from_cartesian(dirs, weights=w.copy())
+    b1 = brdf.create_from_scattering(src, rcv, pf.FrequencyData(s, freqs),
+                                     pf.FrequencyData(alpha, freqs))
+    np.testing.assert_allclose(np.real(b1.freq), g[f"{tag}_brdf_scattering"], rtol=1e-14)
+    np.testing.assert_allclose(rcv.weights, g[f"{tag}_weights_after"], rtol=1e-15)
+    rcv = pf.Coordinates.from_cartesian(dirs, weights=w.copy())
+    b2 = brdf.create_from_scattering(src, rcv, pf.FrequencyData(s, freqs))
+    np.testing.assert_allclose(np.real(b2.freq), g[f"{tag}_brdf_scattering_noabs"], rtol=1e-14)
+    rcv = pf.Coordinates.from_cartesian(dirs, weights=w.copy())
+    b3 = brdf.create_from_directional_scattering(
+        src, rcv, pf.FrequencyData(g[f"{tag}_directional"], freqs),
+        pf.FrequencyData(alpha, freqs))
+    np.testing.assert_allclose(np.real(b3.freq), g[f"{tag}_brdf_directional"], rtol=1e-14)
+    assert np.array_equal(b3.frequencies, freqs)

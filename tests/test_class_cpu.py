@@ -111,3 +111,69 @@ def test_equality_and_checkpoint_of_unbaked_objects():
     out.set_wall_brdf(np.array([1]), pf.FrequencyData(np.ones_like(freqs), freqs),
                       pf.Coordinates(0, 0, 1, weights=1), pf.Coordinates(0, 0, 1, weights=1))
     assert list(out._brdf_index) == [0, 1]
+
+
+def test_direct_sound_matches_the_live_reference():
+    """``calculate_direct_sound`` (RadiosityFast.py:605-657): vectors from the reference's own
+    method (tests/golden/make_golden.py::gen_direct_sound) -- spreading loss and air
+    attenuation to 1e-15, floor delay bins bit-exact.  Host arithmetic: runs without a GPU."""
+    import numpy as np
+    from conftest import load_golden
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    g = load_golden("direct_sound")
+    rad = sp.DirectionalRadiosityFast.from_polygon(sp.testing.shoebox_room_stub(1, 1, 1), 1.0)
+    freqs = np.array([250.0, 1e3, 4e3])
+    rad.set_air_attenuation(pf.FrequencyData(g["air_attenuation"], freqs))
+    rad._source = pf.Coordinates(*g["source"])
+    rad._speed_of_sound = float(g["speed_of_sound"])
+    rad._etc_time_resolution = float(g["dt"])
+    direct, delay = rad.calculate_direct_sound(pf.Coordinates.from_cartesian(g["receivers"]))
+    np.testing.assert_allclose(direct, g["direct_sound"], rtol=1e-15)
+    assert np.array_equal(delay, g["n_sample_delay"])
+    with pytest.raises(ValueError, match="pf.Coordinates"):
+        rad.calculate_direct_sound(g["receivers"])
+
+
+def test_wall_rotation_invariants_of_the_reference_tests():
+    """``_rotate_coords_to_normal`` (RadiosityFast.py:971-986; pyfar's Orientations calls
+    restated on scipy): the invariants the reference's tests state
+    (tests/test_DRadiosityFast.py:153-172: all rotated directions lie in the wall's positive
+    half space; :46-107: two orthogonal walls with flipped up vectors see each other under
+    mirrored directions), the closed-form rotation, and the committed vectors."""
+    import numpy as np
+    from conftest import load_golden
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf
+    from sparrowpy_b200.radiosity import _rotate_coords_to_normal
+    g = load_golden("wall_rotation")
+    coords = pf.Coordinates.from_cartesian(g["dirs"], weights=g["weights"])
+    for n, u, want in zip(g["normals"], g["ups"], g["rotated"]):
+        src, rcv = _rotate_coords_to_normal(n, u, coords, coords)
+        assert src.cshape == coords.cshape and np.array_equal(src.weights, coords.weights)
+        np.testing.assert_allclose(src.cartesian, want, atol=1e-15)
+        np.testing.assert_allclose(rcv.cartesian, want, atol=1e-15)
+        assert (src.cartesian @ n > 0).all()                       # positive half space
+        np.testing.assert_allclose(src.radius, 1.0, atol=1e-15)
+        m = pf.rotation_to_wall_frame(n, u)                        # normal <- z, up <- x
+        np.testing.assert_allclose(src.cartesian, g["dirs"] @ m.T, atol=1e-14)
+        np.testing.assert_allclose(m @ [0, 0, 1], n, atol=1e-15)
+        np.testing.assert_allclose(m @ [1, 0, 0], u, atol=1e-15)
+    # reference test_patch_2_out_dir_mapping: walls x = 0 (up +z) and y = 0 (up -z)
+    samples = np.array([[np.cos(a) * np.sin(c), np.sin(a) * np.sin(c), np.cos(c)]
+                        for c in np.deg2rad([0.0, 45.0, 90.0])
+                        for a in np.deg2rad(np.arange(0, 360, 45))])
+    samples[np.abs(samples) < 1e-15] = 0
+    dirs = pf.Coordinates.from_cartesian(samples, weights=np.ones(len(samples)))
+    o0, _ = _rotate_coords_to_normal([1, 0, 0], [0, 0, 1], dirs, dirs)
+    o1, _ = _rotate_coords_to_normal([0, 1, 0], [0, 0, -1], dirs, dirs)
+    c0, c1 = np.array([0, .5, .5]), np.array([.5, 0, .5])
+    i0 = int(np.argmin(np.linalg.norm(o0.cartesian - (c1 - c0) / np.linalg.norm(c1 - c0), axis=1)))
+    i1 = int(np.argmin(np.linalg.norm(o1.cartesian - (c0 - c1) / np.linalg.norm(c1 - c0), axis=1)))
+    assert i0 == i1                         # symmetry over the x = y plane, up vectors flipped
+    v0, v1 = o0.cartesian[i0], o1.cartesian[i1]
+    np.testing.assert_allclose(v0[2], 0, atol=1e-7)
+    np.testing.assert_allclose(v0, -v1, atol=1e-7)
+    # non-perpendicular view / up is rejected like pf.Orientations.from_view_up
+    with pytest.raises(ValueError, match="perpendicular"):
+        _rotate_coords_to_normal([1, 0, 0], [1, 0, 1], dirs, dirs)

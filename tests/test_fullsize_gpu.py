@@ -102,11 +102,15 @@ def test_c2_exchange_properties(c2):
                                               workspace=ws).dense()).sum())
     e3 = float((h3 - h2).sum())
     assert 0 < e3 < e2
-    # (5) TMA-tiled and CSR stage 1 agree at full size
+    # (5) the default (tensor-memory) and the CSR stage 1 agree at full size
     import os
+    old = os.environ.get("SPB_GATHER")
     os.environ["SPB_GATHER"] = "csr"
     try:
         hc = exchange.energy_exchange(tables, e0, delay0, n_samples, 3, workspace=ws).dense()
         assert float((hc - h3).abs().max() / h3.abs().max()) < 1e-12
     finally:
-        os.environ["SPB_GATHER"] = "tma"
+        if old is None:
+            os.environ.pop("SPB_GATHER", None)
+        else:
+            os.environ["SPB_GATHER"] = old

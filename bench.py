@@ -70,8 +70,9 @@ SPEED_OF_SOUND = 343.2
 DT = 1e-3
 
 
-def build_scene(cfg, dtype):
-    """Bake the scene on the current GPU through the public class API."""
+def build_scene(cfg, dtype, bake=True):
+    """Bake the scene on the current GPU through the public class API (``bake=False``: set
+    the scene up but leave the bake to the caller, e.g. distributed.sharded_bake_tables)."""
     import sparrowpy_b200 as sp
     from sparrowpy_b200 import pyfar_shim as pf, scenes
     kind, arg = cfg["scene"]
@@ -94,7 +95,8 @@ def build_scene(cfg, dtype):
     rad.set_wall_brdf(np.arange(rad.n_walls), pf.FrequencyData(brdf, freqs), coords, coords)
     air = 1e-4 * 2.0 ** np.arange(nb) if nb > 1 else np.zeros(1)
     rad.set_air_attenuation(pf.FrequencyData(air, freqs))
-    rad.bake_geometry()
+    if bake:
+        rad.bake_geometry()
     if "source" in cfg:
         rad.init_source_energy(pf.Coordinates(*cfg["source"]))
     return rad
@@ -280,6 +282,60 @@ def workload_config(cfg, name, n_patches, n_pairs, n_dir, n_band, dtype):
                    f"{hist_bytes / 1e6:.0f} MB, 3 of them + G are streamed per order)"
                    if hist_bytes > 126e6 * 2 else
                    "working set fits L2 (small config, no flush)")}
+
+
+def time_pipeline(cfg, dtype):
+    """Whole pipeline through the public class, host polygons in, mono ETCs (host) out, one
+    cold pass with wall-clock seconds per stage (CUDA-synchronised): the reference's call
+    sequence from_polygon -> set_wall_brdf -> bake_geometry -> init_source_energy ->
+    calculate_energy_exchange -> collect_energy_receiver_mono."""
+    import torch
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import pyfar_shim as pf, scenes
+    stages = {}
+
+    def lap(name, t0):
+        torch.cuda.synchronize()
+        stages[name] = time.perf_counter() - t0
+        return time.perf_counter()
+
+    t_all = t0 = time.perf_counter()
+    kind, arg = cfg["scene"]
+    walls = (scenes.shoebox(*arg) if kind == "shoebox" else scenes.street_canyon(0, arg))
+    rad = sp.DirectionalRadiosityFast.from_polygon([sp.Polygon(*w) for w in walls],
+                                                   cfg["patch"], dtype=dtype)
+    t0 = lap("from_polygon_s", t0)
+    nb = cfg["bands"]
+    freqs = (cfg.get("first_band_hz", 125.0) * 2.0 ** np.arange(nb) if nb > 1
+             else np.array([1000.0]))
+    if cfg["dirs"] is not None:
+        dirs, weights = scenes.hemisphere_directions(*cfg["dirs"])
+    else:
+        dirs, weights = np.array([[0.0, 0.0, 1.0]]), np.array([1.0])
+    brdf = scenes.brdf_from_scattering(dirs, weights, np.full(nb, cfg["scattering"]),
+                                       np.full(nb, cfg["absorption"]))
+    coords = pf.Coordinates.from_cartesian(dirs, weights=weights)
+    rad.set_wall_brdf(np.arange(rad.n_walls), pf.FrequencyData(brdf, freqs), coords, coords)
+    air = 1e-4 * 2.0 ** np.arange(nb) if nb > 1 else np.zeros(1)
+    rad.set_air_attenuation(pf.FrequencyData(air, freqs))
+    t0 = lap("set_wall_brdf_s", t0)
+    rad.bake_geometry()
+    t0 = lap("bake_geometry_s", t0)
+    rad.init_source_energy(pf.Coordinates(*cfg["source"]))
+    t0 = lap("init_source_energy_s", t0)
+    rad._pair_tables(SPEED_OF_SOUND, DT, cfg["n_samples"])
+    t0 = lap("exchange_tables_s", t0)
+    rad.calculate_energy_exchange(SPEED_OF_SOUND, DT, cfg["n_samples"] * DT,
+                                  max_reflection_order=cfg["orders"])
+    t0 = lap("calculate_energy_exchange_s", t0)
+    etc = rad.collect_energy_receiver_mono(
+        pf.Coordinates.from_cartesian(np.array(cfg["receivers"], float)))
+    t0 = lap("collect_energy_receiver_mono_s", t0)
+    return {"stages": stages, "total_s": time.perf_counter() - t_all,
+            "mono_etc_checksum": float(np.sum(etc.time)),
+            "api": "DirectionalRadiosityFast: host polygons in, mono ETCs at the receivers out "
+                   "(one cold pass; exchange_tables_s = index tables built on first use of "
+                   "calculate_energy_exchange, timed apart)"}
 
 
 def load_peaks():
@@ -564,6 +620,12 @@ def main():
                "kind": "port", "sample": res["sample"],
                "seconds_per_etc": res["seconds_per_order"] * orders}
 
+    pipeline = None
+    comm = sx.comm
+    if rank == 0 and world == 1:
+        del sx
+        torch.cuda.empty_cache()
+        pipeline = time_pipeline(cfg, args.dtype)
     if rank == 0:
         line = {
             "metric": "patch-pair*time-bin exchanges/s (energy exchange, s per ETC alongside)",
@@ -578,7 +640,7 @@ def main():
                     "directed_pairs_kept": int(tables.src.numel()),
                     "tile_records": int(tables.n_records),
                     "record_window": int(tables.win_w),
-                    "parallelism": (f"receiver shards x{world}, exchange: {sx.comm}"
+                    "parallelism": (f"receiver shards x{world}, exchange: {comm}"
                                     if world > 1 else "1 GPU")},
             "clocks": clocks.summary(), "roofline": roofline,
         }
@@ -586,6 +648,8 @@ def main():
             line["bake"] = bake_info
         line["e2e"] = e2e
         line["result"] = result
+        if pipeline:
+            line["pipeline"] = pipeline
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -833,18 +897,20 @@ def run_large(args, cfg, rank, world, local_rank, warmup, log):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     t0 = time.time()
-    rad = build_scene(cfg, args.dtype)
-    torch.cuda.synchronize()
-    n_pairs = int(rad._baked["pairs"].shape[0])
-    log(f"baked {args.config}: N={rad.n_patches} P={n_pairs} in {time.time() - t0:.1f}s")
+    rad = build_scene(cfg, args.dtype, bake=False)
     n_samples, orders = cfg["n_samples"], cfg["orders"]
-    tables = rad._pair_tables(SPEED_OF_SOUND, DT, n_samples, n_shards=world,
-                              shard=rank if world > 1 else None)
-    # the per-pair bake tensors of the whole scene (visibility matrix, form factors,
-    # direction indices: ~60 GB for config 5) are not needed once this rank's tables exist
-    rad._baked = None
-    rad._tables = None
+    # the bake itself is sharded: every rank evaluates its rows of the visibility matrix and
+    # the pairs found there, then the directed pairs travel to the owner of their receiver
+    # (distributed.sharded_bake_tables); no rank holds the whole matrix or pair list
+    torch.cuda.reset_peak_memory_stats(dev)
+    tables, n_pairs = distributed.sharded_bake_tables(rad, SPEED_OF_SOUND, DT, n_samples)
+    torch.cuda.synchronize()
+    bake_s = time.time() - t0
+    bake_peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+    log(f"sharded bake {args.config}: N={rad.n_patches} P={n_pairs} in {bake_s:.1f}s, "
+        f"peak {bake_peak_gb:.1f} GB on rank 0")
     torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats(dev)
     code = _lib.dtype_code(args.dtype)
     esize = 8 if code == _lib.F64 else 4
     n_dir, n_band = tables.n_dirs, tables.n_bands
@@ -962,7 +1028,7 @@ def run_large(args, cfg, rank, world, local_rank, warmup, log):
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "kernel": "k_gather_tma + k_mix (one band block, one order)",
+                         "kernel": "k_gather_tmem + k_mix (one band block, one order)",
                          "avg_launch_ms": avg_ms, "launches_timed": launches,
                          "share_of_step": sum(step_ms) / max(elapsed_ms, 1e-9),
                          "algorithmic_bytes_per_launch": alg_bytes,
@@ -975,6 +1041,11 @@ def run_large(args, cfg, rank, world, local_rank, warmup, log):
                     "api": "host E0/d0 -> BandwiseExchange.run -> ShardedHistogram."
                            "collect_mono (all-reduce) -> pinned host"},
             "result_checksum": float(mono_host.double().sum()),
+            "bake": {"sharded_bake_s": bake_s, "peak_memory_gb_rank0": bake_peak_gb,
+                     "note": "visibility rows / form factors / direction indices split over "
+                             "the ranks, directed pairs routed to the receiver's owner by one "
+                             "all-to-all (distributed.sharded_bake_tables)"},
+            "exchange_peak_memory_gb_rank0": torch.cuda.max_memory_allocated(dev) / 1e9,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

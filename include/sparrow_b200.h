@@ -243,6 +243,13 @@ int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blo
                                const void *groups, int64_t n_groups, const int32_t *members,
                                const int32_t *bin_ptr, const int32_t *bin_items, uint8_t *vis,
                                void *stream);
+/* Rows [row_lo, row_hi) of the same matrix into vis_rows ([row_hi - row_lo, N] uint8): the
+ * unit of the bake when it is sharded over GPUs (pair tiles are independent). */
+int spb_visibility_p2p_grouped_rows(const double *centers, int64_t n, const void *blockers,
+                                    const void *groups, int64_t n_groups,
+                                    const int32_t *members, const int32_t *bin_ptr,
+                                    const int32_t *bin_items, int64_t row_lo, int64_t row_hi,
+                                    uint8_t *vis_rows, void *stream);
 /* host twins of spb_make_blockers / spb_visibility_p2p_grouped (HOST pointers): the
  * same predicates compiled for the CPU; used by the CPU tests only */
 int spb_make_blockers_host(const double *surf_points_h, const double *surf_normals_h,

@@ -311,9 +311,11 @@ def visibility_p2p_grouped_host(centers, surf_normals, surf_points, group_ids):
     return vis.astype(bool)
 
 
-def visibility_p2p_grouped(centers, surf_normals, surf_points, group_ids):
+def visibility_p2p_grouped(centers, surf_normals, surf_points, group_ids, row_range=None):
     """``geometry._check_patch2patch_visibility`` (geometry.py:750-797), hierarchical:
-    same (N, N) bool matrix as :func:`visibility_p2p` in O(N^2 * walls)."""
+    same (N, N) bool matrix as :func:`visibility_p2p` in O(N^2 * walls).  ``row_range`` =
+    ``(lo, hi)`` computes those rows only and returns a (hi - lo, N) matrix -- the unit of a
+    bake that is sharded over GPUs."""
     centers = _dev(centers, torch.float64)
     n = centers.shape[0]
     blockers = make_blockers(surf_points, surf_normals)
@@ -323,7 +325,27 @@ def visibility_p2p_grouped(centers, surf_normals, surf_points, group_ids):
         blk_np, group_ids.cpu().numpy() if isinstance(group_ids, torch.Tensor) else group_ids)
     dev = centers.device
     t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
-    vis = torch.empty((n, n), dtype=torch.uint8, device=dev)
-    _lib.call("spb_visibility_p2p_grouped", centers, n, blockers, t(groups), len(groups),
-              t(members), t(bin_ptr), t(bin_items), vis, _lib.stream_ptr())
+    if row_range is None:
+        vis = torch.empty((n, n), dtype=torch.uint8, device=dev)
+        _lib.call("spb_visibility_p2p_grouped", centers, n, blockers, t(groups), len(groups),
+                  t(members), t(bin_ptr), t(bin_items), vis, _lib.stream_ptr())
+        return vis.bool()
+    lo, hi = int(row_range[0]), int(row_range[1])
+    vis = torch.empty((hi - lo, n), dtype=torch.uint8, device=dev)
+    _lib.call("spb_visibility_p2p_grouped_rows", centers, n, blockers, t(groups), len(groups),
+              t(members), t(bin_ptr), t(bin_items), lo, hi, vis, _lib.stream_ptr())
     return vis.bool()
+
+
+def triangle_row_range(n, part, n_parts):
+    """Rows of the upper-triangular visibility matrix for part ``part`` of ``n_parts`` with
+    (nearly) equal numbers of entries: row i holds n - 1 - i pairs."""
+    import numpy as np
+    total = n * (n - 1) // 2
+    rows = np.arange(n + 1, dtype=np.int64)
+    before = rows * (2 * n - rows - 1) // 2          # pairs in rows [0, i)
+    lo = int(np.searchsorted(before, total * part // n_parts, side="left"))
+    hi = int(np.searchsorted(before, total * (part + 1) // n_parts, side="left"))
+    if part == n_parts - 1:
+        hi = n
+    return min(lo, n), min(hi, n)

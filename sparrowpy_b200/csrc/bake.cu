@@ -205,9 +205,10 @@ k_vis_p2p_grouped(const double *__restrict__ centers, int64_t n,
                   const Blocker *__restrict__ blockers, const exact::Group *__restrict__ groups,
                   int32_t n_groups, const int32_t *__restrict__ members,
                   const int32_t *__restrict__ bin_ptr, const int32_t *__restrict__ bin_items,
-                  int64_t chunks_per_row, uint8_t *__restrict__ vis) {
+                  int64_t chunks_per_row, int64_t row_lo, uint8_t *__restrict__ vis) {
+    // rows [row_lo, row_lo + gridDim.x / chunks_per_row) of the matrix; vis holds those rows
     __shared__ exact::Group sg[kMaxGroupsSmem];
-    const int64_t i = blockIdx.x / chunks_per_row;
+    const int64_t i = row_lo + blockIdx.x / chunks_per_row;
     const int64_t j0 = (blockIdx.x % chunks_per_row) * kVisThreads;
     if (j0 + kVisThreads - 1 <= i) return;
     const bool staged = n_groups <= kMaxGroupsSmem;
@@ -232,7 +233,7 @@ k_vis_p2p_grouped(const double *__restrict__ centers, int64_t n,
         visible = !exact::group_blocked(A, B, v, vlen, cull_ok, grp, blockers, members, bin_ptr,
                                         bin_items);
     }
-    vis[i * n + j] = visible ? 1 : 0;
+    vis[(i - row_lo) * n + j] = visible ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -691,7 +692,28 @@ int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blo
     SPB_REQUIRE(n * chunks <= 2147483647LL, "too many patches for one launch");
     k_vis_p2p_grouped<<<(unsigned)(n * chunks), kVisThreads, 0, st>>>(
         centers, n, (const Blocker *)blockers, (const exact::Group *)groups, (int32_t)n_groups,
-        members, bin_ptr, bin_items, chunks, vis);
+        members, bin_ptr, bin_items, chunks, 0, vis);
+    return check_launch("k_vis_p2p_grouped");
+}
+
+int spb_visibility_p2p_grouped_rows(const double *centers, int64_t n, const void *blockers,
+                                    const void *groups, int64_t n_groups,
+                                    const int32_t *members, const int32_t *bin_ptr,
+                                    const int32_t *bin_items, int64_t row_lo, int64_t row_hi,
+                                    uint8_t *vis_rows, void *stream) {
+    SPB_REQUIRE(centers && vis_rows && blockers && groups && members && bin_ptr && bin_items,
+                "null pointer");
+    SPB_REQUIRE(n_groups >= 0 && n_groups <= 2147483647LL, "n_groups");
+    SPB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= n, "row range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows = row_hi - row_lo;
+    if (rows == 0) return 0;
+    SPB_CUDA(cudaMemsetAsync(vis_rows, 0, (size_t)rows * n, st));
+    const int64_t chunks = ceil_div(n, kVisThreads);
+    SPB_REQUIRE(rows * chunks <= 2147483647LL, "too many rows for one launch");
+    k_vis_p2p_grouped<<<(unsigned)(rows * chunks), kVisThreads, 0, st>>>(
+        centers, n, (const Blocker *)blockers, (const exact::Group *)groups, (int32_t)n_groups,
+        members, bin_ptr, bin_items, chunks, row_lo, vis_rows);
     return check_launch("k_vis_p2p_grouped");
 }
 

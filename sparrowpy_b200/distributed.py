@@ -392,3 +392,110 @@ class BandwiseExchange:
                     sx.e_total[src0:src0 + self.own * d])
         return ShardedHistogram(self.total, t, self.n_samples, sx.pad, sx.j_lo, sx.j_hi,
                                 self.own, group=self.group, collect=self.collect)
+
+
+# ---------------------------------------------------------------------------
+# sharded bake: SURVEY.md 8(e) "pair tiles are independent"
+# ---------------------------------------------------------------------------
+def route_directed(dest, int_fields, ff, world, group=None):
+    """Send every directed pair to the rank that owns its receiver: ``dest`` (M,) rank per
+    entry, ``int_fields`` (M, K) int32, ``ff`` (M,) float64.  One variable-size all-to-all
+    per tensor (the only collective of the bake).  Returns the entries this rank received."""
+    order = torch.argsort(dest, stable=True)
+    counts = torch.bincount(dest, minlength=world).to(torch.int64)
+    ints, ff = int_fields[order].contiguous(), ff[order].contiguous()
+    if world == 1:
+        return ints, ff
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts, group=group)
+    send, recv = counts.tolist(), recv_counts.tolist()
+    ints_out = ints.new_empty((sum(recv), ints.shape[1]))
+    ff_out = ff.new_empty(sum(recv))
+    dist.all_to_all_single(ints_out, ints, output_split_sizes=recv, input_split_sizes=send,
+                           group=group)
+    dist.all_to_all_single(ff_out, ff, output_split_sizes=recv, input_split_sizes=send,
+                           group=group)
+    return ints_out, ff_out
+
+
+def sharded_bake_tables(rad, speed_of_sound, dt, n_samples, group=None, part=None,
+                        n_parts=None, route=None):
+    """``bake_geometry`` (RadiosityFast.py:369-433) + the exchange tables of THIS rank's
+    receiver shard, with the bake itself split over the ranks: rank r evaluates the rows
+    ``bake.triangle_row_range(N, r, world)`` of the visibility matrix (equal numbers of
+    (i < j) entries), the form factors, distances and BRDF direction indices of the visible
+    pairs it finds there, and sends each directed pair to the owner of its receiver.  No rank
+    ever holds the (N, N) matrix or the pair list of the whole scene.  The tables are
+    identical to ``rad._pair_tables(..., n_shards=world, shard=rank)`` after an unsharded
+    bake (entries are sorted by (segment, sender) on arrival).
+
+    ``part`` / ``n_parts`` / ``route`` let a single process play several ranks (tests)."""
+    import numpy as np
+    from . import bake, exchange, geometry
+    sharded = dist.is_initialized() and part is None
+    rank = dist.get_rank(group) if sharded else (part or 0)
+    world = dist.get_world_size(group) if sharded else (n_parts or 1)
+    g = rad._geom()
+    dev = rad._device
+    n = rad.n_patches
+    lo, hi = bake.triangle_row_range(n, rank, world)
+    vis_rows = bake.visibility_p2p_grouped(g["center"], g["normal"], g["points"],
+                                           rad._patch_to_wall_ids, row_range=(lo, hi))
+    pairs = bake.visible_pairs(vis_rows)
+    pairs[:, 0] += lo
+    del vis_rows
+    ff, _ = bake.form_factors(g["points"], g["normal"], g["area"], pairs)
+    with_brdf = rad._brdf_incoming_directions is not None
+    if with_brdf:
+        vi, vo, brdf, bidx = rad._brdf_tables()
+        n_in, n_out = vi.shape[1], vo.shape[1]
+        vi_d, vo_d = torch.from_numpy(vi).to(dev), torch.from_numpy(vo).to(dev)
+    else:
+        n_in = n_out = 1
+        vi_d = vo_d = None
+    dist_p, out_dir, in_dir = bake.pair_geometry(g["center"], g["wall_ids"], pairs, vi_d, vo_d)
+    n_bins = 1 if rad._frequencies is None else rad.n_bins
+    air = (np.zeros(n_bins) if rad._air_attenuation is None
+           else np.real(rad._air_attenuation).astype(float))
+    sender, receiver, ff_dir = exchange.directed_pairs(pairs, ff, g["area"])
+    if with_brdf:
+        coef = np.exp(-air)[None, None, :] * brdf.reshape(-1, n_out, n_bins)
+        cls = torch.from_numpy(bidx).to(dev)[g["wall_ids"][sender]] * n_in + in_dir.long()
+    else:
+        coef = np.exp(-air)[None, None, :] * np.ones((1, 1, n_bins))
+        cls = torch.zeros_like(sender)
+    delay = bake.delay_bins(dist_p, speed_of_sound, dt)
+    delay = torch.stack([delay, delay], dim=1).reshape(-1)
+    n_pairs_local = int(pairs.shape[0])
+    del pairs, ff, dist_p, in_dir
+    perm, n_internal = geometry.compact_patch_order(rad._patches_points, rad._patch_to_wall_ids,
+                                                    n_shards=world)
+    perm_d = torch.from_numpy(perm).to(dev)
+    j_lo, j_hi, size = shard_range(n_internal, rank, world)
+    dest = (perm_d[receiver] // size).clamp_(max=world - 1)
+    ints = torch.stack([sender.to(torch.int32), receiver.to(torch.int32),
+                        out_dir.to(torch.int32), cls.to(torch.int32),
+                        delay.to(torch.int32)], dim=1)
+    kept = delay[delay < n_samples]          # pairs with delay >= T never contribute
+    stats = torch.tensor([n_pairs_local, int(kept.max().item()) if kept.numel() else 0],
+                         dtype=torch.int64, device=dev)
+    del kept
+    del sender, receiver, out_dir, cls, delay
+    if route is not None:
+        ints, ff_dir, stats = route(dest, ints, ff_dir, stats)
+    else:
+        ints, ff_dir = route_directed(dest, ints, ff_dir, world, group)
+        if world > 1:
+            n_tot = stats[:1].clone()
+            dist.all_reduce(n_tot, group=group)
+            d_max = stats[1:].clone()
+            dist.all_reduce(d_max, op=dist.ReduceOp.MAX, group=group)
+            stats = torch.cat([n_tot, d_max])
+    n_pairs, max_delay = int(stats[0].item()), int(stats[1].item())
+    tables = exchange.build_pair_tables(
+        ints[:, 0].long(), ints[:, 1].long(), ff_dir, ints[:, 4].long(), ints[:, 2],
+        ints[:, 3].long(), torch.from_numpy(np.ascontiguousarray(coef)).to(dev), n, n_samples,
+        rad._dtype, rank=perm_d, n_internal=n_internal,
+        receiver_range=(j_lo, j_hi) if world > 1 else None,
+        max_delay=max_delay, n_directed=2 * n_pairs)
+    return tables, n_pairs

@@ -120,7 +120,7 @@ def launch_gather(tables, prev, g, cta_order, n_alloc, b_lo, b_hi, j_lo, j_hi, t
 
 def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches,
                       n_samples, dtype, rank=None, n_internal=None, gather=None,
-                      receiver_range=None):
+                      receiver_range=None, max_delay=None, n_directed=None):
     """Sort directed pairs into segments (class, receiver) and drop pairs whose
     delay is >= n_samples (they contribute nothing, RadiosityFast.py:1137-1140).
 
@@ -135,12 +135,13 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
     pairs whose receiver lies in that range -- the tables of one receiver shard of a
     multi-GPU run (distributed.shard_range).  The segment / tile index spaces and
     ``max_delay`` / ``n_directed`` stay those of the whole scene, so that every rank
-    derives the same buffer layout.
+    derives the same buffer layout.  ``max_delay`` / ``n_directed`` override those two
+    quantities when the pair list handed in is already one shard's (sharded bake).
     """
     code = _lib.dtype_code(dtype)
     tdt = _lib.torch_dtype(code)
     n_classes, n_dirs, n_bands = coef.shape
-    n_directed = int(sender.numel())
+    n_directed = int(sender.numel()) if n_directed is None else int(n_directed)
     keep = delay < n_samples
     sender, receiver, ff = sender[keep], receiver[keep], ff[keep]
     delay, out_dir, cls = delay[keep], out_dir[keep], cls[keep]
@@ -149,7 +150,8 @@ def build_pair_tables(sender, receiver, ff, delay, out_dir, cls, coef, n_patches
         rank = rank.to(sender.device).long().contiguous()
         n_patches = int(n_internal)
         sender, receiver = rank[sender.long()], rank[receiver.long()]
-    max_delay = int(delay.max().item()) if delay.numel() else 0
+    if max_delay is None:
+        max_delay = int(delay.max().item()) if delay.numel() else 0
     if receiver_range is not None:
         lo, hi = receiver_range
         own = (receiver >= lo) & (receiver < hi)

@@ -162,3 +162,61 @@ def test_grouped_visibility_full_size_c2():
     grouped = bake.visibility_p2p_grouped(T(cen), T(wn[ids]), T(pts), ids)
     assert torch.equal(brute, grouped)
     assert int(grouped.sum()) == 5672500
+
+
+@pytest.mark.parametrize("name", ["scene_directional", "scene_canyon01", "scene_uneven"])
+@pytest.mark.parametrize("n_parts", [2, 3])
+def test_sharded_bake_builds_the_same_tables(name, n_parts):
+    """distributed.sharded_bake_tables: the bake split by visibility rows over `n_parts`
+    ranks (played by one process; the all-to-all is replaced by an in-memory router) gives
+    exactly the tables of the unsharded bake restricted to each receiver shard."""
+    import sparrowpy_b200 as sp
+    from sparrowpy_b200 import distributed, pyfar_shim as pf
+    g = load_golden(name)
+    walls = [sp.Polygon(p, u, n) for p, u, n in
+             zip(g["walls_points"], g["walls_up"], g["walls_normal"])]
+    rad = sp.DirectionalRadiosityFast.from_polygon(walls, float(g["patch_size"]))
+    if "brdf_dirs" in g:
+        coords = pf.Coordinates.from_cartesian(g["brdf_dirs"], weights=g["brdf_weights"])
+        for m in range(g["brdf"].shape[0]):
+            rad.set_wall_brdf(np.nonzero(g["brdf_index"] == m)[0],
+                              pf.FrequencyData(g["brdf"][m] / np.pi, g["frequencies"]),
+                              coords, coords)
+        rad.set_air_attenuation(pf.FrequencyData(g["air_attenuation"], g["frequencies"]))
+    c, dt = float(g["speed_of_sound"]), float(g["dt"])
+    n_samples = int(float(g["duration"]) / dt)
+    # pass 1: every part computes its rows and posts its directed pairs
+    posted = []
+
+    def collect(dest, ints, ff, stats):
+        posted.append((dest.clone(), ints.clone(), ff.clone(), stats.clone()))
+        return ints[:0], ff[:0], stats
+
+    for part in range(n_parts):
+        distributed.sharded_bake_tables(rad, c, dt, n_samples, part=part, n_parts=n_parts,
+                                        route=collect)
+    dest = torch.cat([p[0] for p in posted])
+    ints = torch.cat([p[1] for p in posted])
+    ff = torch.cat([p[2] for p in posted])
+    stats = torch.stack([torch.stack([p[3][0] for p in posted]).sum(),
+                         torch.stack([p[3][1] for p in posted]).max()])
+    # pass 2: every part receives what was addressed to it (in scrambled order)
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    rad.bake_geometry()
+    assert int(stats[0]) == rad._baked["pairs"].shape[0]
+    for part in range(n_parts):
+        mine = torch.nonzero(dest == part).reshape(-1)
+        mine = mine[torch.randperm(mine.numel(), generator=gen).to(mine.device)]
+
+        def deliver(_d, _i, _f, _s, mine=mine):
+            return ints[mine], ff[mine], stats
+
+        got, n_pairs = distributed.sharded_bake_tables(rad, c, dt, n_samples, part=part,
+                                                       n_parts=n_parts, route=deliver)
+        rad._tables = None
+        want = rad._pair_tables(c, dt, n_samples, n_shards=n_parts, shard=part)
+        assert n_pairs == rad._baked["pairs"].shape[0]
+        assert (got.n_patches, got.max_delay, got.n_directed, got.win_w) == \
+            (want.n_patches, want.max_delay, want.n_directed, want.win_w)
+        for f in ("seg_ptr", "src", "wgt", "dly", "coef", "win_ptr", "win_recs", "rank"):
+            assert torch.equal(getattr(got, f), getattr(want, f)), (part, f)

@@ -55,6 +55,17 @@ for dtype in ("f64", "f32"):
     os.environ["SPB_COMM"] = "p2p"
     part = rad._pair_tables(bench.SPEED_OF_SOUND, bench.DT, n_samples, n_shards=world,
                             shard=rank)
+    # the sharded bake (rows of the visibility matrix per rank + all-to-all of the directed
+    # pairs) must build exactly these tables
+    sb, n_pairs = distributed.sharded_bake_tables(rad, bench.SPEED_OF_SOUND, bench.DT, n_samples)
+    same = n_pairs == rad._baked["pairs"].shape[0] and all(
+        torch.equal(getattr(sb, f), getattr(part, f))
+        for f in ("seg_ptr", "src", "wgt", "dly", "coef", "rank") + (
+            ("win_ptr", "win_recs") if part.win_recs is not None else ("ent_ptr", "recs")))
+    ok &= bool(same)
+    if rank == 0:
+        print(f"{dtype} sharded bake: tables equal={bool(same)}", flush=True)
+    del sb
     for block in (1, 2):
         bx = distributed.BandwiseExchange(part, n_samples, dev, band_block=block)
         h = bx.run(rad._e0_dev, delay0, orders)

@@ -441,17 +441,15 @@ def main():
     st = torch.cuda.current_stream()
     gather_events = []
 
-    def timed_order(prev, cur, total, b_lo, b_hi):
+    def timed_gather(prev, b_lo, b_hi, j_lo=None, j_hi=None):
         cst = torch.cuda.current_stream()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(cst)
-        exchange.launch_gather(sx.t, prev, sx.g, sx.cta_order(), sx.n_alloc, b_lo, b_hi,
-                               sx.j_lo, sx.j_hi, sx.t_pad, sx.ld, sx.pad, kind=gather)
+        sx._gather(prev, b_lo, b_hi, j_lo, j_hi)
         ev1.record(cst)
         gather_events.append((ev0, ev1))
-        sx._mix(cur, total, b_lo, b_hi)
 
-    sx.compute = timed_order
+    sx.gather_fn = timed_gather
 
     def step():
         sx.init(e0_dev, delay0)
@@ -567,7 +565,7 @@ def main():
         api = ("sparrowpy_b200.exchange.energy_exchange_host (host E0/d0 in pinned memory "
                "-> device, K orders, full ETC -> pinned host)")
     else:
-        sx.compute = sx._cuda_order
+        sx.gather_fn = sx._gather
 
         def e2e_step():
             e0 = e0_host.to(dev, non_blocking=True).to(tdt)

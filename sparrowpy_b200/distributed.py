@@ -117,45 +117,57 @@ class ShardedExchange:
             self.cuda and self.comm == "nccl") else None
         self.side_stream = torch.cuda.Stream(device=device) if (
             self.cuda and self.handles is not None) else None
+        self.gather_fn = self._gather
 
     # -- local kernels -------------------------------------------------------
+    def _gather(self, prev, b_lo, b_hi, j_lo=None, j_hi=None):
+        """Stage 1 for bands [b_lo, b_hi) and receivers [j_lo, j_hi) (default: the shard)."""
+        j_lo = self.j_lo if j_lo is None else j_lo
+        j_hi = self.j_hi if j_hi is None else j_hi
+        launch_gather(self.t, prev, self.g, self.cta_order(j_lo, j_hi), self.n_alloc, b_lo,
+                      b_hi, j_lo, j_hi, self.t_pad, self.ld, self.pad)
+
     def _cuda_order(self, prev, cur, total, b_lo, b_hi):
-        launch_gather(self.t, prev, self.g, self.cta_order(), self.n_alloc, b_lo, b_hi,
-                      self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad)
+        self.gather_fn(prev, b_lo, b_hi)
         self._mix(cur, total, b_lo, b_hi)
 
-    def cta_order(self):
-        """Launch order of this rank's tiles: longest record lists first (LPT), so the
-        short tiles fill the tail of the grid."""
-        if getattr(self, "_cta_order", None) is None:
+    def cta_order(self, j_lo=None, j_hi=None):
+        """Launch order of the tiles of receivers [j_lo, j_hi) (default: the shard): longest
+        record lists first (LPT), so the short tiles fill the tail of the grid."""
+        j_lo = self.j_lo if j_lo is None else j_lo
+        j_hi = self.j_hi if j_hi is None else j_hi
+        cache = self.__dict__.setdefault("_cta_orders", {})
+        if (j_lo, j_hi) not in cache:
             t = self.t
-            n_r = 8
+            n_r = SHARD_ALIGN
             n_blocks = -(-t.n_patches // n_r)
-            jb_lo, jb_hi = self.j_lo // n_r, -(-self.j_hi // n_r)
+            jb_lo, jb_hi = j_lo // n_r, -(-j_hi // n_r)
             ptr = t.tile_ptr
             counts = (ptr[1:] - ptr[:-1]).view(t.n_classes, n_blocks)
             local = counts[:, jb_lo:jb_hi].reshape(-1)
-            self._cta_order = torch.argsort(local, descending=True, stable=True).to(
+            cache[(j_lo, j_hi)] = torch.argsort(local, descending=True, stable=True).to(
                 torch.int32).contiguous()
-        return self._cta_order
+        return cache[(j_lo, j_hi)]
 
-    def _mix(self, cur, total, b_lo, b_hi):
+    def _mix(self, cur, total, b_lo, b_hi, j_lo=None, j_hi=None):
         """Stage 2; with symmetric buffers it also delivers E_k to every rank."""
         import ctypes
         t = self.t
         code = _lib.I32(t.dtype)
         st = _lib.stream_ptr()
+        j_lo = self.j_lo if j_lo is None else j_lo
+        j_hi = self.j_hi if j_hi is None else j_hi
         if self.handles is None:
             _lib.call("spb_exchange_mix", self.g, cur, total, t.seg_ptr, t.coef, t.n_patches,
-                      self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, self.j_lo,
-                      self.j_hi, self.t_pad, self.ld, self.pad, code, st)
+                      self.n_alloc, t.n_classes, t.n_dirs, t.n_bands, b_lo, b_hi, j_lo,
+                      j_hi, self.t_pad, self.ld, self.pad, code, st)
             return
         hdl = self.handles[cur.data_ptr()]
         ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in hdl.buffer_ptrs])
         mc = ctypes.c_void_p(int(hdl.multicast_ptr) if self.comm == "multicast" else 0)
         _lib.call("spb_exchange_mix_fused", self.g, ptrs, _lib.I32(self.world), mc, total,
                   t.seg_ptr, t.coef, t.n_patches, self.n_alloc, t.n_classes, t.n_dirs,
-                  t.n_bands, b_lo, b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad,
+                  t.n_bands, b_lo, b_hi, j_lo, j_hi, self.t_pad, self.ld, self.pad,
                   code, st)
 
     def _barrier(self, channel=0):

@@ -216,9 +216,8 @@ def cpu_exchange_rate(rad, cfg, n_threads, budget_s=12.0, log=None):
 
 def time_bake(rad, n_pairs):
     """Device times of the two compute-bound bake kernels on the baked scene (north_star
-    (1)), as fractions of the FP64 pipe from the nominal op counts of SURVEY.md 8d:
-    ~350 flop per full (pair, blocker) visibility test but ~25 for the fast path that
-    decides almost all of them, ~3.3 kflop per Stokes pair."""
+    (1)); their achieved fraction of the FP64 pipe is taken from ncu's instruction counters
+    (profiles/), not from assumed op counts."""
     import torch
     from sparrowpy_b200 import bake
     g = rad._geom()
@@ -254,18 +253,14 @@ def time_bake(rad, n_pairs):
     same = bool(torch.equal(vis, vis_g))
     pairs = rad._baked["pairs"]
     ff_ms = timed(lambda: bake.form_factors(g["points"], g["normal"], g["area"], pairs))
-    pair_blocker = 0.5 * n * (n - 1) * n
-    fp64_peak = 37e12
     return {
         "visibility_ms": vis_grouped_ms, "visibility_groups": int(len(groups)),
         "visibility_bruteforce_ms": vis_ms, "visibility_grouped_equals_bruteforce": same,
-        "pair_blocker_tests_per_s": pair_blocker / (vis_ms * 1e-3),
-        "visibility_fp64_frac_nominal": 25.0 * pair_blocker / (vis_ms * 1e-3) / fp64_peak,
+        "pair_wall_tests_per_s": 0.5 * n * (n - 1) * len(groups) / (vis_grouped_ms * 1e-3),
         "form_factor_ms": ff_ms, "form_factor_pairs_per_s": n_pairs / (ff_ms * 1e-3),
-        "form_factor_fp64_frac_nominal": 3300.0 * n_pairs / (ff_ms * 1e-3) / fp64_peak,
-        "fp64_pipe_nominal_tflops": 37.0,
-        "note": "pair_blocker counts every (i<j, blocker) combination, including those "
-                "skipped by the early exit once a pair is known to be blocked",
+        "note": "FP64-pipe fractions of these kernels come from ncu instruction counters "
+                "(DFMA/DADD/DMUL executed / duration), see profiles/r02_bake_kernels.txt and "
+                "DESIGN.md 3.2-3.3; no nominal op counts are assumed here",
     }
 
 
@@ -449,7 +444,17 @@ def main():
         ev1.record(cst)
         gather_events.append((ev0, ev1))
 
+    def timed_order_fused(prev, cur, total, b_lo, b_hi):
+        cst = torch.cuda.current_stream()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(cst)
+        sx._order_fused(prev, cur, total, b_lo, b_hi)
+        ev1.record(cst)
+        gather_events.append((ev0, ev1))
+
     sx.gather_fn = timed_gather
+    sx.order_fn = timed_order_fused
+    fused = sx.fused_order()
 
     def step():
         sx.init(e0_dev, delay0)
@@ -466,7 +471,7 @@ def main():
     gather_events.clear()
     # gather+mix per (order, band launch) + init (memsets + scatter)
     band_launches = n_band if (world > 1 and sx.comm == "nccl") else 1
-    launches_per_step = orders * band_launches * 2 + 4
+    launches_per_step = orders * band_launches * (1 if fused else 2) + 4
     with ClockSampler(local_rank) as clocks:
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -522,6 +527,8 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     kernel = {"tmem": "k_gather_tmem", "tma": "k_gather_tma", "csr": "k_gather"}[gather]
+    if fused:
+        kernel += " (stage 2 and the delivery of E_k fused into its epilogue)"
     roofline = {
         # the gather is bound by its FMA pipe and the operand path that feeds it, not by HBM
         # (DRAM traffic is a few % of the HBM peak, see `traffic` and profiles/); the
@@ -565,7 +572,7 @@ def main():
         api = ("sparrowpy_b200.exchange.energy_exchange_host (host E0/d0 in pinned memory "
                "-> device, K orders, full ETC -> pinned host)")
     else:
-        sx.gather_fn = sx._gather
+        sx.gather_fn, sx.order_fn = sx._gather, sx._order_fused
 
         def e2e_step():
             e0 = e0_host.to(dev, non_blocking=True).to(tdt)

@@ -153,6 +153,20 @@ int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr
                              int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld,
                              int64_t pad, int64_t window, int dtype, void *stream);
 
+/* One whole reflection order (stage 1 + stage 2, RadiosityFast.py:1121-1144) in ONE kernel for
+ * scenes with a single BRDF class and a single direction (n_classes = n_dirs = 1, e.g. diffuse
+ * walls): the tensor-memory gather scales its sums by coef[b] in its epilogue, adds them to
+ * e_total and stores E_k into the n_peers buffers cur_ptrs_h[0..n_peers) (HOST array of device
+ * addresses: this rank's ping-pong buffer and, for a receiver-sharded run, the peers' -- the
+ * per-order exchange rides on the compute kernel, tile by tile).  Rows of receivers without
+ * pairs are zeroed.  Same result, bit for bit, as spb_exchange_gather_tmem + spb_exchange_mix. */
+int spb_exchange_order_fused(const void *e_prev, const uint64_t *cur_ptrs_h, int n_peers,
+                             void *e_total, const void *coef, const int64_t *ent_ptr,
+                             const void *recs, const int32_t *cta_order, int64_t n_patches,
+                             int64_t n_alloc, int64_t n_bands, int64_t b_lo, int64_t b_hi,
+                             int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad,
+                             int64_t window, int dtype, void *stream);
+
 /* Stage 2 of one order for receiver patches [j_lo, j_hi), bands [b_lo, b_hi): BRDF
  * contraction, writes e_cur rows of those patches and accumulates them into
  * e_total.  coef: [C, D, B] in dtype. */

@@ -255,6 +255,20 @@ struct TmapSet {
     CUtensorMap m[8];
 };
 
+// Stage 2 fused into the stage-1 epilogue for scenes with one BRDF class and one direction
+// (diffuse walls: E_k[j] = coef[b] * G[j]): instead of writing G, a consumer warp scales its
+// accumulators, adds them to E_total and stores E_k into every rank's ping-pong buffer (the
+// rank's own and, over NVLink, the peers'), so that k_mix and its exposed communication
+// disappear and the stores of finished tiles overlap the tiles still running.
+constexpr int kMaxPeers = 8;
+constexpr int kEpiBytes = 8 * 4096;            // one 4 KB transpose buffer per consumer warp
+struct FuseArgs {
+    double *cur[kMaxPeers];    // E_k buffers of all ranks (n == 0: not fused, write G)
+    double *total;             // E_total of this rank
+    const double *coef;        // (1, 1, B)
+    int n;
+};
+
 // Register deal per role (setmaxnreg); launch = 16 warps x 128.
 struct Regs {
     static constexpr int kConsumer = 184;
@@ -268,7 +282,8 @@ struct Regs {
 
 template <int H, int B>
 __global__ void __launch_bounds__(kThreads, 1)
-k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
+k_gather_tmem(const __grid_constant__ TmapSet tmaps, const __grid_constant__ FuseArgs fuse,
+              double *__restrict__ g,
               const int64_t *__restrict__ ent_ptr, const WinRecord *__restrict__ recs,
               const int32_t *__restrict__ cta_order, int64_t n_patches, int64_t n_alloc,
               int64_t n_blocks, int64_t n_dirs, int64_t b_lo, int64_t b_hi, int64_t jb_lo,
@@ -292,15 +307,16 @@ k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
     static_assert(TS >= 2 && S >= 2, "double buffering");
     static_assert(kRing % 16 == 0, "ring alignment");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: S x kStage | record ring | barriers | tmem slot
+    // layout: S x kStage | record ring | epilogue transpose buffers | barriers | tmem slot
     const uint32_t sm_stages = smem_u32(smem_raw);
     const uint32_t sm_recs = sm_stages + S * kStage;
-    const uint32_t sm_full = sm_recs + kRing;                         // smem_full[S]
+    const uint32_t sm_epi = sm_recs + kRing;                          // 8 x 4 KB (fused epilogue)
+    const uint32_t sm_full = sm_epi + kEpiBytes;                      // smem_full[S]
     const uint32_t sm_empty = sm_full + 8 * S;                        // smem_empty[S]
     const uint32_t tm_full = sm_empty + 8 * S;                        // tmem_full[TS][4]
     const uint32_t tm_empty = tm_full + 8 * TS * 4;                   // tmem_empty[TS][4]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(
-        smem_raw + S * kStage + kRing + 16 * S + 64 * TS);
+        smem_raw + S * kStage + kRing + kEpiBytes + 16 * S + 64 * TS);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -313,7 +329,6 @@ k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
     const int64_t tile = c * n_blocks + jb;
     const int64_t e0 = ent_ptr[tile];
     const int n_bat = (int)((ent_ptr[tile + 1] - e0) / B);   // record lists are padded to B
-    if (n_bat == 0) return;                            // no pairs: rows are never read
     const int bands_per_cta = 4 / qpb;
     const int64_t bg = blockIdx.y / n_tchunks;
     const int64_t tc = blockIdx.y - bg * n_tchunks;
@@ -329,6 +344,23 @@ k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
     for (int s = 0; s < bands_per_cta; ++s) n_act_bands += (band0 + s < b_hi) ? 1 : 0;
     const int box_rows = 32 * qpb + 1;
     const int box_stride = (box_rows * 128 + 1023) & ~1023;
+    if (n_bat == 0) {
+        // no pairs.  Not fused: the G rows are never read.  Fused: E_k of these receivers is
+        // zero and must overwrite what the ping-pong buffers hold from two orders ago
+        if (fuse.n > 0) {
+            const double2 zero = make_double2(0.0, 0.0);
+            for (int idx = threadIdx.x; idx < 4 * kR * (kQuarterT / 2); idx += kThreads) {
+                const int q = idx / (kR * (kQuarterT / 2));
+                const int rem = idx - q * (kR * (kQuarterT / 2));
+                const int64_t j = jb * kR + rem / (kQuarterT / 2);
+                const int64_t t = q_t0(q) + 2 * (rem % (kQuarterT / 2));
+                if (!q_active(q) || j >= n_patches || t >= t_pad) continue;
+                const int64_t o = (q_band(q) * n_alloc + j) * ld + pad + t;
+                for (int p = 0; p < fuse.n; ++p) *reinterpret_cast<double2 *>(fuse.cur[p] + o) = zero;
+            }
+        }
+        return;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -514,16 +546,85 @@ k_gather_tmem(const __grid_constant__ TmapSet tmaps, double *__restrict__ g,
             // ---- epilogue: 16 consecutive bins per receiver row ----
             const int64_t b = q_band(q);
             const int64_t t0 = q_t0(q) + (int64_t)lane * kLaneT;
-            if (t0 < t_pad) {
+            if (fuse.n == 0) {
+                if (t0 < t_pad) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int64_t j = jb * kR + grp * 4 + s;
+                        if (j < n_patches) {
+                            double2 *out = reinterpret_cast<double2 *>(
+                                g + ((b * n_classes + c) * n_patches + j) * ld + pad + t0);
+#pragma unroll
+                            for (int k = 0; k < kLaneT / 2; ++k)
+                                out[k] = make_double2(acc[s][2 * k], acc[s][2 * k + 1]);
+                        }
+                    }
+                }
+            } else {
+                // fused stage 2.  The lanes own 16 consecutive bins each (128 bytes apart): the
+                // receiver's 512 bins are transposed through a swizzled 4 KB buffer so that
+                // every store instruction of the warp covers 512 contiguous bytes (full
+                // NVLink / L2 lines), then stored to all ranks and added to E_total.
+                const double cf = fuse.coef[b];
+                const uint32_t epi = sm_epi + (uint32_t)warp * 4096;
+                const int64_t tq = q_t0(q);                      // first bin of the quarter
+                // chunk m = i * 32 + lane of the quarter = bins 2m, 2m + 1; E_total is read for
+                // a whole receiver (8 independent loads per lane) BEFORE the transpose, so that
+                // one memory latency is exposed per receiver instead of one per chunk
+                auto row_of = [&](int s) { return (b * n_alloc + jb * kR + grp * 4 + s) * ld + pad + tq; };
+                auto load_total = [&](int s, double2 (&tot)[8]) {
+                    const bool valid = jb * kR + grp * 4 + s < n_patches;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int m = i * 32 + lane;
+                        tot[i] = (valid && tq + 2 * m < t_pad)
+                                     ? *reinterpret_cast<const double2 *>(fuse.total + row_of(s) + 2 * m)
+                                     : make_double2(0.0, 0.0);
+                    }
+                };
+                double2 tot[8];
+                load_total(0, tot);
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     const int64_t j = jb * kR + grp * 4 + s;
-                    if (j < n_patches) {
-                        double2 *out = reinterpret_cast<double2 *>(
-                            g + ((b * n_classes + c) * n_patches + j) * ld + pad + t0);
+                    __syncwarp();
 #pragma unroll
-                        for (int k = 0; k < kLaneT / 2; ++k)
-                            out[k] = make_double2(acc[s][2 * k], acc[s][2 * k + 1]);
+                    for (int k = 0; k < kLaneT / 2; ++k) {
+                        // E_k = fma(coef, G, 0): the rounding of k_mix
+                        const double e0v = fma(cf, acc[s][2 * k], 0.0);
+                        const double e1v = fma(cf, acc[s][2 * k + 1], 0.0);
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(
+                                         epi + (uint32_t)(lane * 128 + ((k ^ (lane & 7)) << 4))),
+                                     "d"(e0v), "d"(e1v) : "memory");
+                    }
+                    __syncwarp();
+                    double2 e[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int m = i * 32 + lane, ln = m >> 3, ch = m & 7;
+                        lds_f64x2(e[i].x, e[i].y, epi + (uint32_t)(ln * 128 + ((ch ^ (ln & 7)) << 4)));
+                    }
+                    const int64_t row = row_of(s);
+                    if (j < n_patches) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int m = i * 32 + lane;
+                            if (tq + 2 * m >= t_pad) continue;
+                            tot[i].x += e[i].x;
+                            tot[i].y += e[i].y;
+                            *reinterpret_cast<double2 *>(fuse.total + row + 2 * m) = tot[i];
+                        }
+                    }
+                    if (s + 1 < 4) load_total(s + 1, tot);      // in flight during the stores
+                    if (j < n_patches) {
+                        for (int p = 0; p < fuse.n; ++p) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int m = i * 32 + lane;
+                                if (tq + 2 * m < t_pad)
+                                    *reinterpret_cast<double2 *>(fuse.cur[p] + row + 2 * m) = e[i];
+                            }
+                        }
                     }
                 }
             }
@@ -556,7 +657,8 @@ template <int H, int B>
 int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRecord *recs,
            const int32_t *cta_order, int64_t n_patches, int64_t n_alloc, int64_t n_classes,
            int64_t n_dirs, int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
-           int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, cudaStream_t st) {
+           int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad, const FuseArgs &fuse,
+           cudaStream_t st) {
     using C = Cfg<H>;
     const int64_t n_blocks = ceil_div(n_patches, kR);
     const int64_t jb_lo = j_lo / kR, jb_hi = ceil_div(j_hi, kR);
@@ -594,14 +696,14 @@ int launch(const double *e_prev, double *g, const int64_t *ent_ptr, const WinRec
 
     constexpr int S = 8 / B, TS = 512 / (B * C::kCols);
     const size_t smem = (size_t)S * B * kBoxArea + (size_t)(S + TS) * B * sizeof(WinRecord) +
-                        (2 * S + 8 * TS) * sizeof(uint64_t) + 16;
+                        kEpiBytes + (2 * S + 8 * TS) * sizeof(uint64_t) + 16;
     SPB_CUDA(cudaFuncSetAttribute(k_gather_tmem<H, B>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const char *dbg_env = getenv("SPB_TMEM_DBG");   // timing experiments: 1 = consumers idle,
     const int dbg = dbg_env ? atoi(dbg_env) : 0;    // 2 = fill idle (results are wrong)
     dim3 grid((unsigned)n_tiles, (unsigned)(n_bgroups * n_tchunks));
     k_gather_tmem<H, B><<<grid, kThreads, smem, st>>>(
-        tmaps, g, ent_ptr, recs, cta_order, n_patches, n_alloc, n_blocks, n_dirs, b_lo, b_hi,
+        tmaps, fuse, g, ent_ptr, recs, cta_order, n_patches, n_alloc, n_blocks, n_dirs, b_lo, b_hi,
         jb_lo, n_jb, n_classes, t_pad, ld, pad, qpb, n_tchunks, dbg);
     return check_launch("k_gather_tmem");
 }
@@ -624,13 +726,14 @@ int spb_window_geometry(int dtype, int64_t *receivers_per_tile, int64_t *max_win
     return 0;
 }
 
-int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr,
-                             const void *recs, const int32_t *cta_order, int64_t n_patches,
-                             int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
-                             int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
-                             int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad,
-                             int64_t window, int dtype, void *stream) {
-    SPB_REQUIRE(e_prev && g && ent_ptr, "null pointer");
+static int gather_tmem_dispatch(const void *e_prev, void *g, const int64_t *ent_ptr,
+                                const void *recs, const int32_t *cta_order, int64_t n_patches,
+                                int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
+                                int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+                                int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad,
+                                int64_t window, int dtype, const tmg::FuseArgs &fuse,
+                                void *stream) {
+    SPB_REQUIRE(e_prev && ent_ptr && (g || fuse.n > 0), "null pointer");
     SPB_REQUIRE(dtype == SPB_F64, "the tensor-memory gather is FP64 only");
     SPB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= n_patches, "receiver range");
     SPB_REQUIRE(0 <= b_lo && b_lo <= b_hi && b_hi <= n_bands, "band range");
@@ -645,12 +748,45 @@ int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr
     if (window == 4)
         return tmg::launch<4, tmg::kBatch>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
                                            n_classes, n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad,
-                                           ld, pad, st);
+                                           ld, pad, fuse, st);
     if (window == 10)
         return tmg::launch<10, tmg::kBatch>(ep, (double *)g, ent_ptr, r, cta_order, n_patches, n_alloc,
                                             n_classes, n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad,
-                                            ld, pad, st);
+                                            ld, pad, fuse, st);
     return fail(-1, "invalid argument", "window must be 4 or 10");
+}
+
+int spb_exchange_gather_tmem(const void *e_prev, void *g, const int64_t *ent_ptr,
+                             const void *recs, const int32_t *cta_order, int64_t n_patches,
+                             int64_t n_alloc, int64_t n_classes, int64_t n_dirs,
+                             int64_t n_bands, int64_t b_lo, int64_t b_hi, int64_t j_lo,
+                             int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad,
+                             int64_t window, int dtype, void *stream) {
+    tmg::FuseArgs fuse = {};
+    return gather_tmem_dispatch(e_prev, g, ent_ptr, recs, cta_order, n_patches, n_alloc,
+                                n_classes, n_dirs, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld,
+                                pad, window, dtype, fuse, stream);
+}
+
+int spb_exchange_order_fused(const void *e_prev, const uint64_t *cur_ptrs_h, int n_peers,
+                             void *e_total, const void *coef, const int64_t *ent_ptr,
+                             const void *recs, const int32_t *cta_order, int64_t n_patches,
+                             int64_t n_alloc, int64_t n_bands, int64_t b_lo, int64_t b_hi,
+                             int64_t j_lo, int64_t j_hi, int64_t t_pad, int64_t ld, int64_t pad,
+                             int64_t window, int dtype, void *stream) {
+    SPB_REQUIRE(cur_ptrs_h && e_total && coef, "null pointer");
+    SPB_REQUIRE(n_peers >= 1 && n_peers <= tmg::kMaxPeers, "1..8 destination buffers");
+    tmg::FuseArgs fuse = {};
+    for (int p = 0; p < n_peers; ++p) {
+        SPB_REQUIRE(cur_ptrs_h[p] && (cur_ptrs_h[p] & 15) == 0, "destination buffer alignment");
+        fuse.cur[p] = (double *)(uintptr_t)cur_ptrs_h[p];
+    }
+    fuse.total = (double *)e_total;
+    fuse.coef = (const double *)coef;
+    fuse.n = n_peers;
+    return gather_tmem_dispatch(e_prev, nullptr, ent_ptr, recs, cta_order, n_patches, n_alloc, 1,
+                                1, n_bands, b_lo, b_hi, j_lo, j_hi, t_pad, ld, pad, window, dtype,
+                                fuse, stream);
 }
 
 }  // extern "C"

@@ -118,6 +118,7 @@ class ShardedExchange:
         self.side_stream = torch.cuda.Stream(device=device) if (
             self.cuda and self.handles is not None) else None
         self.gather_fn = self._gather
+        self.order_fn = self._order_fused
 
     # -- local kernels -------------------------------------------------------
     def _gather(self, prev, b_lo, b_hi, j_lo=None, j_hi=None):
@@ -128,8 +129,35 @@ class ShardedExchange:
                       b_hi, j_lo, j_hi, self.t_pad, self.ld, self.pad)
 
     def _cuda_order(self, prev, cur, total, b_lo, b_hi):
+        if self.fused_order():
+            self.order_fn(prev, cur, total, b_lo, b_hi)
+            return
         self.gather_fn(prev, b_lo, b_hi)
         self._mix(cur, total, b_lo, b_hi)
+
+    def fused_order(self):
+        """True when one reflection order is ONE kernel: a single BRDF class and direction
+        (diffuse walls) with the tensor-memory gather -- stage 2 and the delivery of E_k to
+        every rank then happen in the gather's epilogue (spb_exchange_order_fused), tile by
+        tile, overlapped with the tiles still running."""
+        t = self.t
+        return (self.cuda and t.win_recs is not None and t.n_classes == 1 and t.n_dirs == 1
+                and self.comm != "multicast"
+                and os.environ.get("SPB_FUSED_ORDER", "1") != "0"
+                and os.environ.get("SPB_GATHER", "tmem") == "tmem")
+
+    def _order_fused(self, prev, cur, total, b_lo, b_hi):
+        import ctypes
+        t = self.t
+        if self.handles is None:
+            dests = [cur.data_ptr()]
+        else:
+            dests = [int(p) for p in self.handles[cur.data_ptr()].buffer_ptrs]
+        ptrs = (ctypes.c_uint64 * len(dests))(*dests)
+        _lib.call("spb_exchange_order_fused", prev, ptrs, _lib.I32(len(dests)), total, t.coef,
+                  t.win_ptr, t.win_recs, self.cta_order(), t.n_patches, self.n_alloc,
+                  t.n_bands, b_lo, b_hi, self.j_lo, self.j_hi, self.t_pad, self.ld, self.pad,
+                  t.win_w, _lib.I32(t.dtype), _lib.stream_ptr())
 
     def cta_order(self, j_lo=None, j_hi=None):
         """Launch order of the tiles of receivers [j_lo, j_hi) (default: the shard): longest

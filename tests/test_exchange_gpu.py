@@ -289,3 +289,35 @@ def test_exchange_invariant_under_patch_renumbering(oracle):
     p0 = exchange.collect_patchwise(ref, rdir, shift, scale)
     assert p1.shape == p0.shape
     assert float((p1 - p0).abs().max() / p0.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["scene_c1", "scene_canyon01", "scene_occluder"])
+def test_fused_order_equals_gather_plus_mix(oracle, name, monkeypatch):
+    """Diffuse scenes (one BRDF class, one direction): the whole reflection order in one
+    kernel (spb_exchange_order_fused: stage 2 in the tensor-memory gather's epilogue) is
+    bit-identical to gather + mix, including rows of receivers without pairs and a receiver
+    sub-range (the sharded case)."""
+    from sparrowpy_b200 import distributed, exchange
+    monkeypatch.setenv("SPB_GATHER", "tmem")
+    g = load_golden(name)
+    out = oracle_run(oracle, g)
+    n_samples = out["etc"].shape[-1]
+    dev = torch.device("cuda:0")
+    tables = device_tables(g, out, "f64", n_samples)
+    assert tables.n_classes == 1 and tables.n_dirs == 1 and tables.win_recs is not None
+    e0 = torch.from_numpy(out["energy_init_source"]).to(dev)
+    c, dt = float(g["speed_of_sound"]), float(g["dt"])
+    delay0 = torch.from_numpy(
+        (out["distance_patches_to_source"] / c / dt).astype(np.int32)).to(dev)
+    orders = int(g["max_order"])
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SPB_FUSED_ORDER", flag)
+        sx = distributed.ShardedExchange(tables, n_samples, dev, local=True)
+        assert sx.fused_order() == (flag == "1")
+        # stale data in the ping-pong buffers must not survive (receivers without pairs)
+        sx.init(e0, delay0)
+        sx.e_b[:, sx.pad:] = 7.0
+        res[flag] = sx.run(orders).dense().clone()
+    assert torch.equal(res["1"], res["0"])
+    assert rel_err(res["1"].cpu().numpy(), out["etc"]) < 1e-6

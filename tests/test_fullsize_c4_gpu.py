@@ -157,3 +157,11 @@ def test_c4_gather_kernels_agree(c4):
     assert float(scale) > 0
     for kind in ("tmem", "tma"):
         assert float((out[kind] - out["csr"]).abs().max() / scale) < 1e-12, kind
+    # C4 is diffuse: the default runs the whole order in one kernel; unfused = bit-identical
+    os.environ["SPB_FUSED_ORDER"] = "0"
+    try:
+        tables = c4._pair_tables(c, dt, n_samples)
+        unfused = exchange.energy_exchange(tables, c4._e0_dev, delay0, n_samples, 3).dense()
+        assert torch.equal(unfused, out["tmem"])
+    finally:
+        os.environ.pop("SPB_FUSED_ORDER", None)

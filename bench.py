@@ -566,9 +566,11 @@ def main():
     out_host = (torch.empty((n, d, b, n_samples), dtype=tdt).pin_memory()
                 if rank == 0 else None)
     if world == 1:
+        ws = exchange.ExchangeWorkspace(tables, n_samples, dev)
+
         def e2e_step():
             exchange.energy_exchange_host(tables, e0_host, d0_host, SPEED_OF_SOUND, DT,
-                                          n_samples, orders, out_host)
+                                          n_samples, orders, out_host, workspace=ws)
         api = ("sparrowpy_b200.exchange.energy_exchange_host (host E0/d0 in pinned memory "
                "-> device, K orders, full ETC -> pinned host)")
     else:

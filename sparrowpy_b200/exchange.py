@@ -433,13 +433,23 @@ class EnergyHistogram:
 
 
 class ExchangeWorkspace:
-    """Device buffers of one exchange run: E_total, ping-pong E_a/E_b and G."""
+    """Device buffers of one exchange run: E_total, ping-pong E_a/E_b and G.  Passing the
+    same workspace to several :func:`energy_exchange` calls re-uses the buffers (the
+    histogram a call returns is then overwritten by the next one)."""
 
     def __init__(self, tables, n_samples, device, need_orders=True):
         t = tables
         self.t_pad, self.pad = _lib.exchange_layout(n_samples, t.max_delay, t.dtype)
         self.ld = self.t_pad + self.pad
         self.n_samples = n_samples
+        self.sx = None
+        if t.win_recs is not None and gather_kind() != "csr":
+            # per-order driver of the tensor-memory gather: it owns the buffers
+            from .distributed import ShardedExchange
+            self.sx = ShardedExchange(t, n_samples, device, need_orders=need_orders, local=True)
+            self.e_total, self.e_a, self.e_b, self.g = (
+                self.sx.e_total, self.sx.e_a, self.sx.e_b, self.sx.g)
+            return
         tdt = _lib.torch_dtype(t.dtype)
         rows = t.n_bands * t.n_patches * t.n_dirs
         self.e_total = torch.empty((rows, self.ld), dtype=tdt, device=device)
@@ -462,7 +472,7 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
     if e0.dim() == 4:
         return _energy_exchange_batch(tables, e0, delay0, n_samples, max_order)
     if tables.win_recs is not None and gather_kind() != "csr":
-        return _energy_exchange_orders(tables, e0, delay0, n_samples, max_order)
+        return _energy_exchange_orders(tables, e0, delay0, n_samples, max_order, workspace)
     t = tables
     tdt = _lib.torch_dtype(t.dtype)
     device = e0.device
@@ -480,12 +490,17 @@ def energy_exchange(tables, e0, delay0, n_samples, max_order, workspace=None):
                            tables=t)
 
 
-def _energy_exchange_orders(tables, e0, delay0, n_samples, max_order):
+def _energy_exchange_orders(tables, e0, delay0, n_samples, max_order, workspace=None):
     """One source through the per-order driver (gather + mix launched from Python) --
     the path of the tensor-memory gather (``spb_energy_exchange`` drives the tiled and CSR
     kernels).  Single device, whatever process group may be initialised."""
     from .distributed import ShardedExchange
-    sx = ShardedExchange(tables, n_samples, e0.device, need_orders=max_order >= 1, local=True)
+    if workspace is not None and workspace.sx is not None and (
+            workspace.sx.e_a is not None or max_order < 1):
+        sx = workspace.sx
+    else:
+        sx = ShardedExchange(tables, n_samples, e0.device, need_orders=max_order >= 1,
+                             local=True)
     sx.init(e0, delay0)
     return sx.run(max(0, int(max_order)))
 

@@ -159,24 +159,30 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU baseline: the oracle port of `_energy_exchange` on a bounded pair sample
 # ---------------------------------------------------------------------------
-def cpu_exchange_rate(rad, cfg, n_threads, budget_s=12.0, log=None):
+def exchange_inputs(rad):
+    """The baked arrays the CPU arms need, as numpy (from a baked + sourced object)."""
+    b = rad._baked
+    return dict(n_patches=np.int64(rad.n_patches), pairs=b["pairs"].cpu().numpy(),
+                e0=rad._energy_init_source, d0=rad._distance_patches_to_source,
+                coef=b["coef"].cpu().numpy(), ff_dir=b["ff_dir"].cpu().numpy(),
+                cls=b["cls"].cpu().numpy(), out_dir=b["out_dir"].cpu().numpy().astype(np.int64),
+                dist=b["dist"].cpu().numpy())
+
+
+def cpu_exchange_rate(inp, cfg, n_threads, budget_s=12.0, log=None):
     """Time the oracle's `_energy_exchange` (one order) on a random subset of the
     visible pairs and extrapolate to the full pair list (work is exactly linear in
-    the number of pairs and orders, RadiosityFast.py:1121-1144).
+    the number of pairs and orders, RadiosityFast.py:1121-1144).  ``inp``: the arrays of
+    :func:`exchange_inputs`.
 
     Returns dict(value=exchanges/s for the full configuration, ...)."""
     from oracle import oracle as orc
-    b = rad._baked
-    n, t_len = rad.n_patches, cfg["n_samples"]
-    pairs = b["pairs"].cpu().numpy()
+    t_len = cfg["n_samples"]
+    pairs = inp["pairs"]
     p_full = pairs.shape[0]
-    e0 = rad._energy_init_source
-    d0 = rad._distance_patches_to_source
-    coef = b["coef"].cpu().numpy()
-    ff_dir = b["ff_dir"].cpu().numpy()
-    cls = b["cls"].cpu().numpy()
-    out_dir = b["out_dir"].cpu().numpy().astype(np.int64)
-    delay = np.repeat((b["dist"].cpu().numpy() / SPEED_OF_SOUND / DT).astype(np.int64), 2)
+    e0, d0, coef, ff_dir, cls, out_dir = (inp[k] for k in ("e0", "d0", "coef", "ff_dir", "cls",
+                                                           "out_dir"))
+    delay = np.repeat((inp["dist"] / SPEED_OF_SOUND / DT).astype(np.int64), 2)
     rng = np.random.default_rng(0)
 
     def run(n_sample, orders=1):
@@ -378,6 +384,9 @@ def main():
                     help="stage-1 kernel: tensor-memory windows (f64; f32 falls back to tma), "
                          "TMA-staged tiles or CSR")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bake-to", default=None,
+                    help="bake the configuration's scene and write the arrays the CPU arm "
+                         "needs to this .npz (used by --impl reference in a child process)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -393,11 +402,15 @@ def main():
         if args.verbose and rank == 0:
             print(f"[bench] {msg}", file=sys.stderr, flush=True)
 
-    import torch
-
+    if args.bake_to:
+        rad = build_scene(cfg, "f64")
+        np.savez(args.bake_to, **exchange_inputs(rad))
+        return
     if args.impl == "reference":
         run_reference(args, cfg, rank, world, log)
         return
+    import torch
+
     if cfg.get("large"):
         run_large(args, cfg, rank, world, local_rank, max(args.warmup, 3), log)
         return
@@ -622,7 +635,7 @@ def main():
     # -- CPU baseline on the host cores (rank 0, N = 1 only) ----------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        res = cpu_exchange_rate(rad, cfg, n_threads=1, log=log)
+        res = cpu_exchange_rate(exchange_inputs(rad), cfg, n_threads=1, log=log)
         cpu = {"value": res["value"], "unit": "pair*bin exchanges/s", "cores": 1,
                "kind": "port", "sample": res["sample"],
                "seconds_per_etc": res["seconds_per_order"] * orders}
@@ -1061,34 +1074,66 @@ def run_large(args, cfg, rank, world, local_rank, warmup, log):
 
 def run_reference(args, cfg, rank, world, log):
     """CPU arm: the oracle port of the reference's `_energy_exchange` on the host
-    cores (all threads), bounded sample per step."""
+    cores (all threads), bounded sample per step.  The scene's baked arrays are INPUTS of
+    this arm: they are produced by a child process (`bench.py --bake-to file`, the CUDA
+    bake -- the CPU oracle would need hours for the visibility of 19 200 patches) and read
+    back as numpy, so that this process never loads the CUDA library and nothing of the
+    GPU path is inside or beside the timed region."""
     if rank != 0:
         return
-    import torch
+    import tempfile
     from oracle import oracle as orc
     orc.build()
-    if not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference",
-                          "unavailable": "scene baking needs the CUDA path; no GPU here"}))
+    if cfg.get("kind") == "c3":                 # no patch pairs: host geometry is all it needs
+        import sparrowpy_b200 as sp
+        from sparrowpy_b200 import scenes
+        half = cfg["scene"][1] / 2
+        rad = sp.DirectionalRadiosityFast.from_polygon(
+            [sp.Polygon(*w) for w in scenes.ground_plane(-half, half, -half, half)], cfg["patch"])
+        srcs = grid_points(*cfg["sources_grid"], half)
+        rcvs = grid_points(*cfg["receivers_grid"], half)
+        res = cpu_c3_rate(rad, cfg, srcs, rcvs, log, budget_s=20.0)
+        print(json.dumps({
+            "impl": "reference", "metric": "source*receiver*patch*band*bin contributions/s "
+            "(order-0 ETCs at all receivers; BASELINE config 3)", "value": res["value"],
+            "unit": "contributions/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": cfg["desc"], "name": args.config},
+            "cpu_baseline": res,
+            "e2e": {"value": res["value"], "unit": "contributions/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}), flush=True)
         return
-    rad = build_scene(cfg, "f64")
-    torch.cuda.synchronize()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "baked.npz")
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE")}
+        child = subprocess.run([sys.executable, os.path.abspath(__file__), "--config",
+                                args.config, "--bake-to", path], env=env,
+                               capture_output=True, text=True)
+        if child.returncode != 0 or not os.path.exists(path):
+            why = (child.stderr.strip().splitlines() or ["bake failed"])[-1][:200]
+            print(json.dumps({"impl": "reference",
+                              "unavailable": f"scene baking needs the CUDA path: {why}"}))
+            return
+        inp = dict(np.load(path))
+    n_patches = int(inp["n_patches"])
+    n_pairs = int(inp["pairs"].shape[0])
+    n_dir, n_band = int(inp["coef"].shape[1]), int(inp["coef"].shape[2])
     # thread count set explicitly (torchrun exports OMP_NUM_THREADS=1; the oracle's
     # `num_threads` clause does not depend on it): every core this process may run on
     threads = max(1, len(os.sched_getaffinity(0)))
-    n_pairs = int(rad._baked["pairs"].shape[0])
-    n_dir, n_band = int(rad._baked["coef"].shape[1]), int(rad._baked["coef"].shape[2])
     orders = cfg["orders"]
     x_per_step = 2.0 * n_pairs * cfg["n_samples"] * orders
     budget = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
     vals = []
     res = None
     for k in range(args.warmup + args.steps):
-        res = cpu_exchange_rate(rad, cfg, n_threads=threads, budget_s=budget, log=log)
+        res = cpu_exchange_rate(inp, cfg, n_threads=threads, budget_s=budget, log=log)
         if k >= args.warmup:
             vals.append(res["value"])
     value = float(np.mean(vals)) if vals else float("nan")
-    one = cpu_exchange_rate(rad, cfg, n_threads=1, budget_s=6.0, log=log)
+    one = cpu_exchange_rate(inp, cfg, n_threads=1, budget_s=6.0, log=log)
     line = {
         "impl": "reference",
         "metric": "patch-pair*time-bin exchanges/s (energy exchange, s per ETC alongside)",
@@ -1097,7 +1142,7 @@ def run_reference(args, cfg, rank, world, log):
         "ms_per_step": x_per_step / value * 1e3 if value == value else None,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(cfg, args.config, rad.n_patches, n_pairs, n_dir, n_band,
+        "config": workload_config(cfg, args.config, n_patches, n_pairs, n_dir, n_band,
                                   "f64"),
         "cpu_baseline": {"value": value, "unit": "pair*bin exchanges/s", "cores": threads,
                          "kind": "port", "sample": res["sample"] if res else "",
@@ -1108,7 +1153,8 @@ def run_reference(args, cfg, rank, world, log):
         "note": "oracle port of _energy_exchange (time-sliced over all host threads, "
                 "bit-identical to the serial reference order); the reference itself is "
                 "single-threaded here (RadiosityFast.py:1396) -- value_1core is the like-for-"
-                "like figure; the scene is baked by the CUDA path (inputs only, not timed)",
+                "like figure; the scene's baked arrays are inputs, produced by a child process "
+                "(CUDA bake) -- this process never loads the CUDA library",
     }
     print(json.dumps(line), flush=True)
 

@@ -247,14 +247,14 @@ def time_bake(rad, n_pairs):
                                      _lib.stream_ptr()), reps=1)
     # hierarchical variant (the one bake_geometry uses): tables built once, kernel timed
     import numpy as _np
-    groups, members, bin_ptr, bin_items = bake.build_groups(
+    groups, members, bin_ptr, bin_items, strips = bake.build_groups(
         blockers.cpu().numpy().reshape(n, -1), rad._patch_to_wall_ids)
     dev = g["center"].device
-    gt, mt, bp, bi = (torch.from_numpy(_np.ascontiguousarray(a)).to(dev)
-                      for a in (groups, members, bin_ptr, bin_items))
+    gt, mt, bp, bi, sp = (torch.from_numpy(_np.ascontiguousarray(a)).to(dev)
+                          for a in (groups, members, bin_ptr, bin_items, strips))
     vis_g = torch.empty_like(vis)
     vis_grouped_ms = timed(lambda: _lib.call(
-        "spb_visibility_p2p_grouped", g["center"], n, blockers, gt, len(groups), mt, bp, bi,
+        "spb_visibility_p2p_grouped", g["center"], n, blockers, gt, len(groups), mt, bp, bi, sp,
         vis_g, _lib.stream_ptr()), reps=1)
     same = bool(torch.equal(vis, vis_g))
     pairs = rad._baked["pairs"]
@@ -727,6 +727,7 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
         torch.ones((1, vo.shape[1], n_band), dtype=torch.float64, device=dev), n, n_samples,
         args.dtype)
     ev = {k: [] for k in ("source", "init", "factors", "collect")}
+    last = {}
 
     def timed(key, fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -748,6 +749,7 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
         rt = timed("factors", lambda: bake.receiver_factors(
             rcv_d, g["center"], g["points"], rvis, air, g["wall_ids"], vo_d, SPEED_OF_SOUND, DT,
             n_samples))
+        last["hist"] = hist
         return timed("collect", lambda: exchange.collect_mono(
             hist, rt["rdir"], rt["shift"], rt["scale"]))
 
@@ -816,6 +818,33 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
         cpu = cpu_c3_rate(rad, cfg, srcs, rcvs_all, log)
     if rank == 0:
         c_ms = stage_ms["collect"]
+        clk = clocks.summary()
+        staged = exchange.collect_kind(last["hist"], len(rcvs))[0] == "staged"
+        # k_collect_staged reads one shared-memory operand per FMA: its roof is the SM's
+        # 128 B/clk shared-memory path (a quarter of the FP64 pipe), at the SM clock sampled
+        # during the timed region.  k_collect_partial reads the operand from L2/HBM.
+        lsu_peak = 128.0 * 148 * float(clk.get("sm_mhz") or 1965.0) * 1e6 / 1e9
+        achieved = alg_bytes / (c_ms * 1e-3) / 1e9
+        peak = lsu_peak if staged else hbm_peak
+        roof = {
+            "bound": "lsu" if staged else "hbm",
+            "kernel": "k_collect_staged" if staged else "k_collect_partial",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None,
+            "peak_source": ("128 B/clk/SM shared-memory operand path x 148 SMs x the SM clock "
+                            "sampled in the timed region" if staged
+                            else "measured (MEASURED_PEAKS.json hbm_gbs)"),
+            "avg_launch_ms": c_ms, "share_of_step": c_ms / ms_per_step,
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "compulsory_hbm_bytes_per_launch": compulsory,
+            "compulsory_hbm_frac_of_peak": compulsory / (c_ms * 1e-3) / 1e9 / hbm_peak,
+            "fma_tflops": 2.0 * fma / (c_ms * 1e-3) / 1e12,
+            "fma_frac_of_measured_pipe": 2.0 * fma / (c_ms * 1e-3) / 1e12 / pipe["tflops"],
+            "fma_pipe_measured_tflops": pipe["tflops"],
+            "note": "algorithmic bytes = one histogram element per (source, receiver, patch, "
+                    "band, bin) contribution (SURVEY 8d); the staged kernel reads each of them "
+                    "from shared memory (the row of a (source, patch) is fetched once per "
+                    "group of 16 receivers), so the operand path, not HBM, is the roof"}
         line = {
             "metric": "source*receiver*patch*band*bin contributions/s (order-0 ETCs at all "
                       "receivers; BASELINE config 3)",
@@ -832,21 +861,8 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
                              f"{compulsory / 1e9:.1f} GB)"},
             "run": {"parallelism": f"receivers sharded x{world}" if world > 1 else "1 GPU",
                     "stage_ms": stage_ms},
-            "clocks": clocks.summary(),
-            "roofline": {
-                "bound": "hbm", "kernel": "k_collect_partial",
-                "achieved": alg_bytes / (c_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": alg_bytes / (c_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                "avg_launch_ms": c_ms, "share_of_step": c_ms / ms_per_step,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "compulsory_bytes_per_launch": compulsory,
-                "fma_tflops": 2.0 * fma / (c_ms * 1e-3) / 1e12,
-                "fma_frac_of_measured_pipe": 2.0 * fma / (c_ms * 1e-3) / 1e12 / pipe["tflops"],
-                "fma_pipe_measured_tflops": pipe["tflops"],
-                "note": "algorithmic bytes = one histogram element per (source, receiver, "
-                        "patch, band, bin) contribution (SURVEY 8d); the rows of a band are "
-                        "shared by all receivers through L2, so frac can exceed 1 -- the "
-                        "compulsory HBM traffic is the histogram once"},
+            "clocks": clk,
+            "roofline": roof,
             "e2e": {"value": x_per_step / e2e_s, "unit": "contributions/s",
                     "h2d_bytes_per_step": int((srcs.size + rcvs.size) * 8),
                     "d2h_bytes_per_step": int(etc.size * 8), "ms_per_step": e2e_s * 1e3,

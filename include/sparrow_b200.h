@@ -218,6 +218,19 @@ int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *sh
                      int64_t ld, int64_t pad, void *mono, void *partial, int64_t n_split,
                      int dtype, void *stream);
 
+/* The same sum for MANY receivers of a diffuse scene (n_dirs = 1, so `rdir` is all zeros and
+ * is not passed): every histogram row is staged once in shared memory and applied to a group
+ * of receivers from there (k_collect_staged) instead of being re-read per receiver -- the
+ * reference loops over the receivers in Python (RadiosityFast.py:711).  shape: receivers x bins
+ * per thread, 0 = auto, 1 = 16x4, 2 = 8x4, 3 = 8x8; n_stages: depth of the cp.async ring,
+ * 0 = auto, else 2..4.  Fails (-1) when a row does not fit shared memory; `partial` and the
+ * result layout are those of spb_collect_mono. */
+int spb_collect_mono_staged(const void *e_total, const int32_t *shift, const void *scale,
+                            int64_t n_receivers, int64_t n_patches, int64_t n_alloc,
+                            int64_t n_bands, int64_t n_samples, int64_t ld, int64_t pad,
+                            void *mono, void *partial, int64_t n_split, int shape,
+                            int n_stages, int dtype, void *stream);
+
 /* patch-wise variant (`collect_energy_receiver_patchwise`, RadiosityFast.py:660):
  * out: [R, N, B, T] dense. */
 int spb_collect_patchwise(const void *e_total, const int32_t *rdir,
@@ -248,22 +261,25 @@ int spb_visibility_p2p(const double *centers, int64_t n, const void *blockers, i
 /* Same result as spb_visibility_p2p, evaluated hierarchically: the blockers are
  * grouped by plane (the patches of one wall), a group is decided with one evaluation
  * of the plane quantities, and only the members whose polygon the plane hit can touch
- * (found through bins along the in-plane y axis) are evaluated individually.
- * O(N^2 * walls) instead of O(N^3).  Tables from sparrowpy_b200.bake.build_groups:
- * groups: n_groups records of spb_group_bytes() bytes; members: blocker indices;
- * bin_ptr / bin_items: CSR of the bins of all groups. */
+ * (found through a 2-D grid of cells over the wall's in-plane coordinates; bins along
+ * the in-plane y axis for the rare query point whose +x ray grazes a horizontal edge)
+ * are evaluated individually.  O(N^2 * walls) instead of O(N^3).  Tables from
+ * sparrowpy_b200.bake.build_groups: groups: n_groups records of spb_group_bytes() bytes;
+ * members: blocker indices; bin_ptr / bin_items: CSR of the y-bins and cells of all groups
+ * (+ the per-bin first-strip index); strips: [lo, hi] pairs of the grazing y-ranges. */
 size_t spb_group_bytes(void);
 int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blockers,
                                const void *groups, int64_t n_groups, const int32_t *members,
-                               const int32_t *bin_ptr, const int32_t *bin_items, uint8_t *vis,
-                               void *stream);
+                               const int32_t *bin_ptr, const int32_t *bin_items,
+                               const double *strips, uint8_t *vis, void *stream);
 /* Rows [row_lo, row_hi) of the same matrix into vis_rows ([row_hi - row_lo, N] uint8): the
  * unit of the bake when it is sharded over GPUs (pair tiles are independent). */
 int spb_visibility_p2p_grouped_rows(const double *centers, int64_t n, const void *blockers,
                                     const void *groups, int64_t n_groups,
                                     const int32_t *members, const int32_t *bin_ptr,
-                                    const int32_t *bin_items, int64_t row_lo, int64_t row_hi,
-                                    uint8_t *vis_rows, void *stream);
+                                    const int32_t *bin_items, const double *strips,
+                                    int64_t row_lo, int64_t row_hi, uint8_t *vis_rows,
+                                    void *stream);
 /* host twins of spb_make_blockers / spb_visibility_p2p_grouped (HOST pointers): the
  * same predicates compiled for the CPU; used by the CPU tests only */
 int spb_make_blockers_host(const double *surf_points_h, const double *surf_normals_h,
@@ -271,7 +287,8 @@ int spb_make_blockers_host(const double *surf_points_h, const double *surf_norma
 int spb_visibility_p2p_grouped_host(const double *centers_h, int64_t n, const void *blockers_h,
                                     const void *groups_h, int64_t n_groups,
                                     const int32_t *members_h, const int32_t *bin_ptr_h,
-                                    const int32_t *bin_items_h, uint8_t *vis_h);
+                                    const int32_t *bin_items_h, const double *strips_h,
+                                    uint8_t *vis_h);
 
 /* `_check_point2patch_visibility` (geometry.py:799-839) for a batch of points:
  * vis[r,j] ([R,N] uint8). */

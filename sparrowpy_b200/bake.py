@@ -215,7 +215,27 @@ def probe_basic_visibility(a, b, surf_points, surf_normals):
 # ---------------------------------------------------------------------------
 _BLK = dict(n=slice(0, 3), s0=slice(3, 6), r0=slice(6, 9), r1=slice(9, 12), xmin=32, xmax=33,
             ymin=34, ymax=35, h=36, aa2d=37)
-_BIN_MARGIN = 2e-3          # members are binned with this margin around their ray band
+# exact::Group (csrc/vis_group.cuh): 17 doubles, then int32 fields from byte 136
+_GRP_BYTES = 176
+_GRP_D = dict(n=slice(0, 3), s0=slice(3, 6), r0=slice(6, 9), r1=slice(9, 12), plane_dev=12,
+              y0=13, inv_bin_h=14, x0=15, inv_bin_w=16)
+_GRP_I = dict(n_bins=34, bin_ptr0=35, m0=36, m1=37, n_bx=38, cell_ptr0=39, strip0=40,
+              n_strips=41, sfirst0=42)
+_BIN_MARGIN = 2e-3          # members are listed with this margin around their ray band
+_MIN_CELL_MEMBERS = 16      # smaller groups keep the 1-D bins only
+
+
+def _csr_lists(first, last, n_lists, values):
+    """CSR of `n_lists` lists where element k (payload values[k]) is a member of the lists
+    first[k] .. last[k]; within a list the elements keep their order.  Returns (ptr, items)."""
+    import numpy as np
+    cnt = np.maximum(last - first + 1, 0)
+    rep = np.repeat(np.arange(len(cnt)), cnt)
+    off = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    lst = first[rep] + off
+    order = np.argsort(lst, kind="stable")
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(lst, minlength=n_lists))])
+    return ptr.astype(np.int64), values[rep][order]
 
 
 def build_groups(blockers_np, group_ids):
@@ -225,19 +245,24 @@ def build_groups(blockers_np, group_ids):
     each blocker belongs to.  A wall becomes one group when all its blockers share the
     bitwise-same normal (hence rotation) and their first vertices lie in one plane to
     within 1e-12; otherwise its blockers become singleton groups (always correct, just
-    not accelerated).  Returns numpy arrays (groups uint8 (G, group_bytes), members
-    int32, bin_ptr int32, bin_items int32).
+    not accelerated).  Per group: bins along the in-plane y axis listing every member of the
+    band, and -- for groups of >= 16 members -- a 2-D grid of cells listing the members whose
+    expanded bounding box touches the cell, plus the y-ranges ("strips") in which a point far
+    to the left of an axis-aligned member can still be a candidate (the kernel then scans the
+    bin instead of the cell).  Returns numpy arrays (groups uint8 (G, group_bytes), members
+    int32, bin_ptr int32, bin_items int32, strips float64 (n, 2)).
     """
     import numpy as np
     lib = _lib.load()
     lib.spb_group_bytes.restype = ctypes.c_size_t
     gbytes = int(lib.spb_group_bytes())
-    assert gbytes == 144, gbytes
+    assert gbytes == _GRP_BYTES, gbytes
     blk = np.ascontiguousarray(blockers_np, dtype=np.float64)
     ids = np.asarray(group_ids)
     member_lists = []
-    for w in np.unique(ids):
-        idx = np.nonzero(ids == w)[0]
+    order = np.argsort(ids, kind="stable")
+    cuts = np.nonzero(np.diff(ids[order]))[0] + 1
+    for idx in np.split(order, cuts):
         key = blk[idx][:, :12].copy()
         key[:, 3:6] = 0.0                                 # n, r0, r1 must be bitwise equal
         same = (key.view(np.uint64) == key[:1].view(np.uint64)).all()
@@ -247,35 +272,106 @@ def build_groups(blockers_np, group_ids):
             member_lists.append((idx, float(dev) + 1e-13))
         else:
             member_lists.extend((idx[k:k + 1], 0.0) for k in range(len(idx)))
-    groups = np.zeros((len(member_lists), gbytes), dtype=np.uint8)
-    gd = groups.view(np.float64).reshape(len(member_lists), gbytes // 8)
-    gi = groups.view(np.int32).reshape(len(member_lists), gbytes // 4)
-    members, bin_ptr, bin_items = [], [0], []
+    n_groups = len(member_lists)
+    groups = np.zeros((n_groups, gbytes), dtype=np.uint8)
+    gd = groups.view(np.float64).reshape(n_groups, gbytes // 8)
+    gi = groups.view(np.int32).reshape(n_groups, gbytes // 4)
+    members, ptr_parts, item_parts, strip_parts = [], [], [], []
+    n_ptr = n_items = n_members = n_strips_all = 0
+
+    def add_lists(ptr, items):
+        """Append one CSR block to bin_ptr / bin_items; returns its offset into bin_ptr."""
+        nonlocal n_ptr, n_items
+        at = n_ptr
+        ptr_parts.append(ptr + n_items)                   # len(lists) + 1 entries
+        item_parts.append(items)
+        n_ptr += len(ptr)
+        n_items += len(items)
+        return at
+
     for g, (idx, dev) in enumerate(member_lists):
         b = blk[idx]
-        lo = b[:, _BLK["ymin"]] - b[:, _BLK["h"]] - _BIN_MARGIN
-        hi = b[:, _BLK["ymax"]] + b[:, _BLK["h"]] + _BIN_MARGIN
+        idx32 = idx.astype(np.int32)
+        h = b[:, _BLK["h"]]
+        lo = b[:, _BLK["ymin"]] - h - _BIN_MARGIN
+        hi = b[:, _BLK["ymax"]] + h + _BIN_MARGIN
         bin_h = float((hi - lo).max())
         y0 = float(lo.min())
         n_bins = int(np.floor((hi.max() - y0) / bin_h)) + 1
         first = np.floor((lo - y0) / bin_h).astype(np.int64)
         last = np.minimum(np.floor((hi - y0) / bin_h).astype(np.int64), n_bins - 1)
-        per_bin = [[] for _ in range(n_bins)]
-        for k in range(len(idx)):
-            # one extra bin on each side guards the rounding of the kernel's bin index
-            for bb in range(max(int(first[k]) - 1, 0), min(int(last[k]) + 1, n_bins - 1) + 1):
-                per_bin[bb].append(int(idx[k]))
-        gd[g, 0:3], gd[g, 3:6] = b[0, _BLK["n"]], b[0, _BLK["s0"]]
-        gd[g, 6:9], gd[g, 9:12] = b[0, _BLK["r0"]], b[0, _BLK["r1"]]
-        gd[g, 12], gd[g, 13], gd[g, 14] = dev, y0, 1.0 / bin_h
-        gi[g, 32], gi[g, 33] = n_bins, len(bin_ptr) - 1
-        gi[g, 34], gi[g, 35] = len(members), len(members) + len(idx)
-        members.extend(int(k) for k in idx)
-        for items in per_bin:
-            bin_items.extend(items)
-            bin_ptr.append(len(bin_items))
-    return (groups, np.asarray(members, np.int32), np.asarray(bin_ptr, np.int32),
-            np.asarray(bin_items if bin_items else [0], np.int32))
+        # one extra bin on each side guards the rounding of the kernel's bin index
+        first, last = np.maximum(first - 1, 0), np.minimum(last + 1, n_bins - 1)
+        ptr, items = _csr_lists(first, last, n_bins, idx32)
+        gd[g, _GRP_D["n"]], gd[g, _GRP_D["s0"]] = b[0, _BLK["n"]], b[0, _BLK["s0"]]
+        gd[g, _GRP_D["r0"]], gd[g, _GRP_D["r1"]] = b[0, _BLK["r0"]], b[0, _BLK["r1"]]
+        gd[g, _GRP_D["plane_dev"]], gd[g, _GRP_D["y0"]] = dev, y0
+        gd[g, _GRP_D["inv_bin_h"]] = 1.0 / bin_h
+        gi[g, _GRP_I["n_bins"]], gi[g, _GRP_I["bin_ptr0"]] = n_bins, add_lists(ptr, items)
+        gi[g, _GRP_I["m0"]], gi[g, _GRP_I["m1"]] = n_members, n_members + len(idx)
+        members.append(idx32)
+        n_members += len(idx)
+        if len(idx) < _MIN_CELL_MEMBERS:
+            continue
+        # --- 2-D cells: members whose expanded box [xlo, xhi] x [lo, hi] touches the cell.  A
+        # member that is not an exactly axis-aligned rectangle is a candidate for every point
+        # to its left (ray rule only), so it is listed in all the cells left of it as well.
+        aa = b[:, _BLK["aa2d"]] != 0.0
+        xlo = b[:, _BLK["xmin"]] - _BIN_MARGIN
+        xhi = b[:, _BLK["xmax"]] + h + _BIN_MARGIN
+        bin_w = float((xhi - xlo).max())
+        x0 = float(xlo.min())
+        inv_w, inv_h = 1.0 / bin_w, gd[g, _GRP_D["inv_bin_h"]]
+        n_bx = int(np.floor((xhi.max() - x0) * inv_w)) + 1
+        if n_bx * n_bins > 4 * len(idx) + 64:              # degenerate spread: not worth it
+            continue
+        # the kernel computes floor((q - origin) * inv) with the same two IEEE operations, which
+        # are monotonic in q; the extra 1e-6 makes ulp-level differences irrelevant
+        bx0 = np.where(aa, np.floor((xlo - 1e-6 - x0) * inv_w), 0.0).astype(np.int64)
+        bx1 = np.floor((xhi + 1e-6 - x0) * inv_w).astype(np.int64)
+        by0 = np.floor((lo - 1e-6 - y0) * inv_h).astype(np.int64)
+        by1 = np.floor((hi + 1e-6 - y0) * inv_h).astype(np.int64)
+        bx0, bx1 = np.clip(bx0, 0, n_bx - 1), np.clip(bx1, 0, n_bx - 1)
+        by0, by1 = np.clip(by0, 0, n_bins - 1), np.clip(by1, 0, n_bins - 1)
+        # expand over the rows first, then over the columns of each (member, row)
+        rptr, mem_row = _csr_lists(by0, by1, n_bins, np.arange(len(idx)))
+        rows_of = np.repeat(np.arange(n_bins), np.diff(rptr))
+        cell_first = rows_of * n_bx + bx0[mem_row]
+        cell_last = rows_of * n_bx + bx1[mem_row]
+        cptr, citems = _csr_lists(cell_first, cell_last, n_bx * n_bins, idx32[mem_row])
+        # --- strips: y-ranges where a point left of an axis-aligned member grazes an edge
+        sl = np.concatenate([lo[aa], b[aa, _BLK["ymax"]] - _BIN_MARGIN])
+        sh = np.concatenate([b[aa, _BLK["ymin"]] + _BIN_MARGIN, hi[aa]])
+        o = np.argsort(sl, kind="stable")
+        sl, sh = sl[o], sh[o]
+        if len(sl):
+            run_hi = np.maximum.accumulate(sh)
+            start = np.concatenate([[True], sl[1:] > run_hi[:-1]])      # a gap before strip k
+            seg = np.cumsum(start) - 1
+            s_lo = sl[start]
+            s_hi = np.full(len(s_lo), -np.inf)
+            np.maximum.at(s_hi, seg, sh)
+        else:
+            s_lo = s_hi = np.zeros(0)
+        edges = y0 + (np.arange(n_bins) * bin_h) - 1e-6    # lower edge of each bin, with slack
+        sfirst = np.searchsorted(s_hi, edges, side="left").astype(np.int64)
+        gd[g, _GRP_D["x0"]], gd[g, _GRP_D["inv_bin_w"]] = x0, inv_w
+        gi[g, _GRP_I["n_bx"]], gi[g, _GRP_I["cell_ptr0"]] = n_bx, add_lists(cptr, citems)
+        gi[g, _GRP_I["strip0"]], gi[g, _GRP_I["n_strips"]] = n_strips_all, len(s_lo)
+        # the per-bin first-strip indices ride in bin_ptr as a list block without items
+        ptr_parts.append(sfirst)
+        gi[g, _GRP_I["sfirst0"]] = n_ptr
+        n_ptr += len(sfirst)
+        strip_parts.append(np.stack([s_lo, s_hi], 1))
+        n_strips_all += len(s_lo)
+    assert n_ptr < 2 ** 31 and n_items < 2 ** 31
+    cat = lambda parts, dt: (np.concatenate(parts).astype(dt) if parts  # noqa: E731
+                             else np.zeros(0, dt))
+    bin_items = cat(item_parts, np.int32)
+    strips = np.concatenate(strip_parts + [np.zeros((1, 2))])           # never empty
+    return (groups, cat(members, np.int32), cat(ptr_parts, np.int32),
+            bin_items if len(bin_items) else np.zeros(1, np.int32),
+            np.ascontiguousarray(strips, dtype=np.float64))
 
 
 def make_blockers_host(surf_points, surf_normals):
@@ -300,13 +396,13 @@ def visibility_p2p_grouped_host(centers, surf_normals, surf_points, group_ids):
     lib = _lib.load()
     cen = np.ascontiguousarray(centers, dtype=np.float64)
     blk = make_blockers_host(surf_points, surf_normals)
-    groups, members, bin_ptr, bin_items = build_groups(blk, group_ids)
+    groups, members, bin_ptr, bin_items, strips = build_groups(blk, group_ids)
     n = cen.shape[0]
     vis = np.zeros((n, n), np.uint8)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     rc = lib.spb_visibility_p2p_grouped_host(p(cen), ctypes.c_int64(n), p(blk), p(groups),
                                              ctypes.c_int64(len(groups)), p(members),
-                                             p(bin_ptr), p(bin_items), p(vis))
+                                             p(bin_ptr), p(bin_items), p(strips), p(vis))
     assert rc == 0
     return vis.astype(bool)
 
@@ -321,19 +417,19 @@ def visibility_p2p_grouped(centers, surf_normals, surf_points, group_ids, row_ra
     blockers = make_blockers(surf_points, surf_normals)
     m = surf_points.shape[0]
     blk_np = blockers.cpu().numpy().reshape(m, -1)
-    groups, members, bin_ptr, bin_items = build_groups(
+    groups, members, bin_ptr, bin_items, strips = build_groups(
         blk_np, group_ids.cpu().numpy() if isinstance(group_ids, torch.Tensor) else group_ids)
     dev = centers.device
     t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
     if row_range is None:
         vis = torch.empty((n, n), dtype=torch.uint8, device=dev)
         _lib.call("spb_visibility_p2p_grouped", centers, n, blockers, t(groups), len(groups),
-                  t(members), t(bin_ptr), t(bin_items), vis, _lib.stream_ptr())
+                  t(members), t(bin_ptr), t(bin_items), t(strips), vis, _lib.stream_ptr())
         return vis.bool()
     lo, hi = int(row_range[0]), int(row_range[1])
     vis = torch.empty((hi - lo, n), dtype=torch.uint8, device=dev)
     _lib.call("spb_visibility_p2p_grouped_rows", centers, n, blockers, t(groups), len(groups),
-              t(members), t(bin_ptr), t(bin_items), lo, hi, vis, _lib.stream_ptr())
+              t(members), t(bin_ptr), t(bin_items), t(strips), lo, hi, vis, _lib.stream_ptr())
     return vis.bool()
 
 

@@ -198,14 +198,18 @@ k_vis_pt2p(const double *__restrict__ points, const double *__restrict__ centers
 
 // hierarchical variant: one CTA per (row i, chunk of j), loop over blocker groups
 // (vis_group.cuh); the group headers are staged in shared memory when they fit
-constexpr int kMaxGroupsSmem = 256;
+constexpr int kMaxGroupsSmem = 128;
 
-__global__ void __launch_bounds__(kVisThreads)
+// kMinBlocks: resident CTAs per SM the register allocation is bounded for (3: no spills;
+// 4: 128 registers, a few spills -- SPB_VIS_MINBLOCKS=4, tools/sweep_vis.py)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kVisThreads, kMinBlocks)
 k_vis_p2p_grouped(const double *__restrict__ centers, int64_t n,
                   const Blocker *__restrict__ blockers, const exact::Group *__restrict__ groups,
                   int32_t n_groups, const int32_t *__restrict__ members,
                   const int32_t *__restrict__ bin_ptr, const int32_t *__restrict__ bin_items,
-                  int64_t chunks_per_row, int64_t row_lo, uint8_t *__restrict__ vis) {
+                  const double *__restrict__ strips, int64_t chunks_per_row, int64_t row_lo,
+                  uint8_t *__restrict__ vis) {
     // rows [row_lo, row_lo + gridDim.x / chunks_per_row) of the matrix; vis holds those rows
     __shared__ exact::Group sg[kMaxGroupsSmem];
     const int64_t i = row_lo + blockIdx.x / chunks_per_row;
@@ -231,7 +235,7 @@ k_vis_p2p_grouped(const double *__restrict__ centers, int64_t n,
     for (int32_t g = 0; g < n_groups && visible; ++g) {
         const exact::Group &grp = staged ? sg[g] : groups[g];
         visible = !exact::group_blocked(A, B, v, vlen, cull_ok, grp, blockers, members, bin_ptr,
-                                        bin_items);
+                                        bin_items, strips);
     }
     vis[(i - row_lo) * n + j] = visible ? 1 : 0;
 }
@@ -651,6 +655,23 @@ __global__ void k_probe_basic_visibility(const double *__restrict__ A,
 
 using namespace spb;
 
+static int launch_vis_grouped(unsigned grid, cudaStream_t st, const double *centers, int64_t n,
+                              const void *blockers, const void *groups, int64_t n_groups,
+                              const int32_t *members, const int32_t *bin_ptr,
+                              const int32_t *bin_items, const double *strips, int64_t chunks,
+                              int64_t row_lo, uint8_t *vis) {
+    const char *env = getenv("SPB_VIS_MINBLOCKS");
+    if (env && env[0] == '4')
+        k_vis_p2p_grouped<4><<<grid, kVisThreads, 0, st>>>(
+            centers, n, (const Blocker *)blockers, (const exact::Group *)groups,
+            (int32_t)n_groups, members, bin_ptr, bin_items, strips, chunks, row_lo, vis);
+    else
+        k_vis_p2p_grouped<3><<<grid, kVisThreads, 0, st>>>(
+            centers, n, (const Blocker *)blockers, (const exact::Group *)groups,
+            (int32_t)n_groups, members, bin_ptr, bin_items, strips, chunks, row_lo, vis);
+    return check_launch("k_vis_p2p_grouped");
+}
+
 extern "C" {
 
 size_t spb_blocker_bytes(int64_t m) { return sizeof(Blocker) * (size_t)(m > 0 ? m : 0); }
@@ -680,29 +701,28 @@ int spb_visibility_p2p(const double *centers, int64_t n, const void *blockers, i
 
 int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blockers,
                                const void *groups, int64_t n_groups, const int32_t *members,
-                               const int32_t *bin_ptr, const int32_t *bin_items, uint8_t *vis,
-                               void *stream) {
-    SPB_REQUIRE(centers && vis && blockers && groups && members && bin_ptr && bin_items,
-                "null pointer");
+                               const int32_t *bin_ptr, const int32_t *bin_items,
+                               const double *strips, uint8_t *vis, void *stream) {
+    SPB_REQUIRE(centers && vis && blockers && groups && members && bin_ptr && bin_items &&
+                strips, "null pointer");
     SPB_REQUIRE(n_groups >= 0 && n_groups <= 2147483647LL, "n_groups");
     cudaStream_t st = (cudaStream_t)stream;
     SPB_CUDA(cudaMemsetAsync(vis, 0, (size_t)n * n, st));
     if (n < 2) return 0;
     const int64_t chunks = ceil_div(n, kVisThreads);
     SPB_REQUIRE(n * chunks <= 2147483647LL, "too many patches for one launch");
-    k_vis_p2p_grouped<<<(unsigned)(n * chunks), kVisThreads, 0, st>>>(
-        centers, n, (const Blocker *)blockers, (const exact::Group *)groups, (int32_t)n_groups,
-        members, bin_ptr, bin_items, chunks, 0, vis);
-    return check_launch("k_vis_p2p_grouped");
+    return launch_vis_grouped((unsigned)(n * chunks), st, centers, n, blockers, groups, n_groups,
+                              members, bin_ptr, bin_items, strips, chunks, 0, vis);
 }
 
 int spb_visibility_p2p_grouped_rows(const double *centers, int64_t n, const void *blockers,
                                     const void *groups, int64_t n_groups,
                                     const int32_t *members, const int32_t *bin_ptr,
-                                    const int32_t *bin_items, int64_t row_lo, int64_t row_hi,
-                                    uint8_t *vis_rows, void *stream) {
-    SPB_REQUIRE(centers && vis_rows && blockers && groups && members && bin_ptr && bin_items,
-                "null pointer");
+                                    const int32_t *bin_items, const double *strips,
+                                    int64_t row_lo, int64_t row_hi, uint8_t *vis_rows,
+                                    void *stream) {
+    SPB_REQUIRE(centers && vis_rows && blockers && groups && members && bin_ptr && bin_items &&
+                strips, "null pointer");
     SPB_REQUIRE(n_groups >= 0 && n_groups <= 2147483647LL, "n_groups");
     SPB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= n, "row range");
     cudaStream_t st = (cudaStream_t)stream;
@@ -711,10 +731,9 @@ int spb_visibility_p2p_grouped_rows(const double *centers, int64_t n, const void
     SPB_CUDA(cudaMemsetAsync(vis_rows, 0, (size_t)rows * n, st));
     const int64_t chunks = ceil_div(n, kVisThreads);
     SPB_REQUIRE(rows * chunks <= 2147483647LL, "too many rows for one launch");
-    k_vis_p2p_grouped<<<(unsigned)(rows * chunks), kVisThreads, 0, st>>>(
-        centers, n, (const Blocker *)blockers, (const exact::Group *)groups, (int32_t)n_groups,
-        members, bin_ptr, bin_items, chunks, row_lo, vis_rows);
-    return check_launch("k_vis_p2p_grouped");
+    return launch_vis_grouped((unsigned)(rows * chunks), st, centers, n, blockers, groups,
+                              n_groups, members, bin_ptr, bin_items, strips, chunks, row_lo,
+                              vis_rows);
 }
 
 size_t spb_group_bytes(void) { return sizeof(exact::Group); }
@@ -734,8 +753,9 @@ int spb_make_blockers_host(const double *surf_points_h, const double *surf_norma
 int spb_visibility_p2p_grouped_host(const double *centers_h, int64_t n, const void *blockers_h,
                                     const void *groups_h, int64_t n_groups,
                                     const int32_t *members_h, const int32_t *bin_ptr_h,
-                                    const int32_t *bin_items_h, uint8_t *vis_h) {
-    SPB_REQUIRE(centers_h && vis_h && blockers_h && groups_h, "null pointer");
+                                    const int32_t *bin_items_h, const double *strips_h,
+                                    uint8_t *vis_h) {
+    SPB_REQUIRE(centers_h && vis_h && blockers_h && groups_h && strips_h, "null pointer");
     const Blocker *blockers = (const Blocker *)blockers_h;
     const exact::Group *groups = (const exact::Group *)groups_h;
     for (int64_t i = 0; i < n; ++i)
@@ -749,7 +769,8 @@ int spb_visibility_p2p_grouped_host(const double *centers_h, int64_t n, const vo
                 bool visible = true;
                 for (int64_t g = 0; g < n_groups && visible; ++g)
                     visible = !exact::group_blocked(A, B, v, sqrt(vv), vv > 1e-6, groups[g],
-                                                    blockers, members_h, bin_ptr_h, bin_items_h);
+                                                    blockers, members_h, bin_ptr_h, bin_items_h,
+                                                    strips_h);
                 out = visible ? 1 : 0;
             }
             vis_h[i * n + j] = out;

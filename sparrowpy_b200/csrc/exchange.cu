@@ -215,6 +215,159 @@ k_collect_partial(const T *__restrict__ e_total, const int32_t *__restrict__ rdi
     }
 }
 
+// ---------------------------------------------------------------------------
+// receiver collection for MANY receivers of a diffuse scene (D = 1): the histogram row of a
+// (band, patch) is staged ONCE in shared memory (cp.async ring, the receivers' scale and shift
+// riding along) and applied to kRcv receivers from there -- k_collect_partial re-reads the
+// row from L2/HBM for every receiver.  256 threads; a thread owns kBins output bins
+// (t = chunk*256*kBins + tid + 256 q) of kRcv receivers: kRcv*kBins accumulators and one
+// conflict-free shared-memory operand per FMA (the 128 B/clk/SM shared-memory path is the
+// roof: a quarter of the FP64 pipe).  The row is stored TWICE back to back, so the circular
+// read E[(t - shift) mod T] is the plain read row2[t - shift + T]: per receiver one address,
+// per bin an immediate offset.  Same partial-sum layout as k_collect_partial.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async_16(uint32_t smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(gmem) : "memory");
+}
+template <int kBytes>
+__device__ __forceinline__ void cp_async_small(uint32_t smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem), "l"(gmem),
+                 "n"(kBytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_pending(int n) {   // n = groups left in flight
+    if (n <= 0) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+}
+
+template <typename T, int kRcv, int kBins>
+__global__ void __launch_bounds__(256)
+k_collect_staged(const T *__restrict__ e_total, const int32_t *__restrict__ shift,
+                 const T *__restrict__ scale, int n_receivers, int64_t n_patches,
+                 int64_t n_alloc, int n_bands, int n_samples, int64_t ld, int64_t pad,
+                 T *__restrict__ partial, int n_split, int n_rgroups, int n_chunks,
+                 int n_stages) {
+    // blockIdx.x = ((band * n_split + split) * n_chunks + chunk) * n_rgroups + rgroup: the CTAs
+    // that read the same histogram rows are neighbours in launch order and meet in L2
+    int64_t id = blockIdx.x;
+    const int rg = (int)(id % n_rgroups); id /= n_rgroups;
+    const int chunk = (int)(id % n_chunks); id /= n_chunks;
+    const int split = (int)(id % n_split);
+    const int b = (int)(id / n_split);
+    const int r0 = rg * kRcv;
+    const int tid = threadIdx.x;
+    const int t0 = chunk * 256 * kBins + tid;
+    const int64_t k_lo = n_patches * split / n_split;
+    const int n_k = (int)(n_patches * (split + 1) / n_split - k_lo);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kVec = 16 / (int)sizeof(T);
+    // one stage: [t_al - T, t_al) copy A | [t_al, t_al + T) copy B | ... up to t_al + row_elems
+    // (read by tail threads only) | kRcv scales | kRcv byte offsets.  A multiple of 16 bytes.
+    const int t_al = (n_samples + kVec - 1) / kVec * kVec;
+    const int n_vec = t_al / kVec;                        // 16-byte pieces of a row
+    const int row_elems = n_chunks * 256 * kBins;         // >= n_samples
+    const int row2 = t_al + row_elems;
+    const int stage_bytes = (row2 + kRcv) * (int)sizeof(T) + kRcv * 4;
+    const bool aligned = t_al == n_samples;               // copy A starts on a 16-byte boundary
+    const uint32_t smem0 = smem_addr(smem_raw);
+    // bins past copy B are read by tail threads only (t >= n_samples, never stored); zero them
+    // once so that no stale bit pattern is ever multiplied (the pieces of copy B may spill
+    // kVec - 1 elements into this zone: finite values of the row's padding)
+    for (int s = 0; s < n_stages; ++s) {
+        T *row = reinterpret_cast<T *>(smem_raw + (size_t)s * stage_bytes);
+        for (int i = 2 * t_al + tid; i < row2; i += 256) row[i] = T(0);
+    }
+
+    auto issue = [&](int i) {                  // patch k_lo + i -> stage i % n_stages
+        const int so = (i % n_stages) * stage_bytes;
+        const int64_t k = k_lo + i;
+        const T *src = e_total + ((int64_t)b * n_alloc + k) * ld + pad;
+        for (int v = tid; v < n_vec; v += 256) {
+            cp_async_16(smem0 + so + (t_al + v * kVec) * (int)sizeof(T), src + (size_t)v * kVec);
+            if (aligned) cp_async_16(smem0 + so + v * 16, src + (size_t)v * kVec);
+        }
+        if (!aligned)                           // copy A element by element
+            for (int v = tid; v < n_samples; v += 256)
+                cp_async_small<(int)sizeof(T)>(
+                    smem0 + so + (t_al - n_samples + v) * (int)sizeof(T), src + v);
+        if (tid < kRcv) {
+            T *sc = reinterpret_cast<T *>(smem_raw + so + (size_t)row2 * sizeof(T));
+            int32_t *off = reinterpret_cast<int32_t *>(sc + kRcv);
+            const int r = r0 + tid;
+            T c = T(0);
+            int32_t h = 0;
+            if (r < n_receivers) {
+                const int64_t rk = (int64_t)r * n_patches + k;
+                c = scale[rk * n_bands + b];
+                h = shift[rk];                 // 0 <= h < n_samples
+            }
+            sc[tid] = c;                       // plain stores, published by the __syncthreads
+            off[tid] = (t_al - h) * (int)sizeof(T);   // that precedes the stage's first read
+        }
+    };
+
+    T acc[kRcv][kBins];
+#pragma unroll
+    for (int r = 0; r < kRcv; ++r)
+#pragma unroll
+        for (int q = 0; q < kBins; ++q) acc[r][q] = T(0);
+
+    for (int i = 0; i < n_stages - 1; ++i) {
+        if (i < n_k) issue(i);
+        cp_async_commit();
+    }
+    for (int i = 0; i < n_k; ++i) {
+        cp_async_wait_pending(n_stages - 2);   // the copies of patch i have landed
+        __syncthreads();                       // ... for every thread; patch i-1 is consumed
+        if (i + n_stages - 1 < n_k) issue(i + n_stages - 1);   // refills the stage of patch i-1
+        cp_async_commit();
+        const unsigned char *st = smem_raw + (size_t)(i % n_stages) * stage_bytes;
+        const unsigned char *mine = st + (size_t)t0 * sizeof(T);
+        const T *sc = reinterpret_cast<const T *>(st) + row2;
+        const int4 *off4 = reinterpret_cast<const int4 *>(sc + kRcv);
+        T c[kRcv];
+        int off[kRcv];
+#pragma unroll
+        for (int r = 0; r < kRcv; r += kVec) {
+            const int4 raw = *reinterpret_cast<const int4 *>(sc + r);   // kVec scales
+            const T *cv = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) c[r + j] = cv[j];
+        }
+#pragma unroll
+        for (int r = 0; r < kRcv; r += 4) {
+            const int4 o = off4[r / 4];
+            off[r] = o.x; off[r + 1] = o.y; off[r + 2] = o.z; off[r + 3] = o.w;
+        }
+#pragma unroll
+        for (int r = 0; r < kRcv; ++r) {
+            const T *win = reinterpret_cast<const T *>(mine + off[r]);
+#pragma unroll
+            for (int q = 0; q < kBins; ++q) acc[r][q] += win[256 * q] * c[r];
+        }
+    }
+    cp_async_wait_pending(0);
+#pragma unroll
+    for (int r = 0; r < kRcv; ++r) {
+        if (r0 + r >= n_receivers) continue;
+        const int64_t rb = (int64_t)(r0 + r) * n_bands + b;
+        T *dst = partial + ((int64_t)split * n_receivers * n_bands + rb) * n_samples;
+#pragma unroll
+        for (int q = 0; q < kBins; ++q) {
+            const int t = t0 + 256 * q;
+            if (t < n_samples) dst[t] = acc[r][q];
+        }
+    }
+}
+
 template <typename T>
 __global__ void k_collect_reduce(const T *__restrict__ partial, T *__restrict__ mono,
                                  int64_t n_out, int64_t n_split) {
@@ -328,6 +481,37 @@ int mix_dispatch(const void *g, void *e_cur, const uint64_t *peer_ptrs_h, int n_
 }  // namespace spb
 
 using namespace spb;
+
+template <typename T, int kRcv, int kBins>
+static int collect_staged_t(const void *e_total, const int32_t *shift, const void *scale,
+                            int64_t n_receivers, int64_t n_patches, int64_t n_alloc,
+                            int64_t n_bands, int64_t n_samples, int64_t ld, int64_t pad,
+                            void *mono, void *partial, int64_t n_split, int n_stages,
+                            cudaStream_t st) {
+    const int64_t n_chunks = ceil_div(n_samples, 256 * kBins);
+    const int64_t n_rgroups = ceil_div(n_receivers, kRcv);
+    constexpr int64_t kVec = 16 / (int64_t)sizeof(T);
+    const int64_t row2 = round_up(n_samples, kVec) + n_chunks * 256 * kBins;   // doubled row
+    const int64_t stage_bytes = (row2 + kRcv) * (int64_t)sizeof(T) + kRcv * 4;
+    if (n_stages == 0) n_stages = 3 * stage_bytes <= 100 * 1024 ? 3 : 2;
+    SPB_REQUIRE(n_stages >= 2 && n_stages <= 4, "n_stages must be 2..4");
+    const int64_t smem = n_stages * stage_bytes;
+    SPB_REQUIRE(smem <= 220 * 1024, "histogram rows too long for shared-memory staging");
+    const int64_t n_cta = n_bands * n_split * n_chunks * n_rgroups;
+    SPB_REQUIRE(n_cta <= 2147483647LL, "grid too large");
+    auto kern = k_collect_staged<T, kRcv, kBins>;
+    SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)n_cta, 256, (size_t)smem, st>>>(
+        (const T *)e_total, shift, (const T *)scale, (int)n_receivers, n_patches, n_alloc,
+        (int)n_bands, (int)n_samples, ld, pad, (T *)partial, (int)n_split, (int)n_rgroups,
+        (int)n_chunks, n_stages);
+    int rc = check_launch("k_collect_staged");
+    if (rc) return rc;
+    const int64_t n_out = n_receivers * n_bands * n_samples;
+    k_collect_reduce<T><<<(unsigned)ceil_div(n_out, 256), 256, 0, st>>>(
+        (const T *)partial, (T *)mono, n_out, n_split);
+    return check_launch("k_collect_reduce");
+}
 
 extern "C" {
 
@@ -526,6 +710,35 @@ int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *sh
         return check_launch("k_collect_reduce");
     }
     return fail(-1, "invalid argument", "dtype");
+}
+
+int spb_collect_mono_staged(const void *e_total, const int32_t *shift, const void *scale,
+                            int64_t n_receivers, int64_t n_patches, int64_t n_alloc,
+                            int64_t n_bands, int64_t n_samples, int64_t ld, int64_t pad,
+                            void *mono, void *partial, int64_t n_split, int shape,
+                            int n_stages, int dtype, void *stream) {
+    SPB_REQUIRE(e_total && shift && scale && mono && partial, "null pointer");
+    SPB_REQUIRE(n_split >= 1 && n_split <= 65535, "n_split");
+    SPB_REQUIRE(n_samples >= 1 && n_samples < (1 << 30), "n_samples");
+    SPB_REQUIRE(dtype == SPB_F64 || dtype == SPB_F32, "dtype");
+    if (n_receivers == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (shape == 0) shape = n_samples <= 1024 ? 1 : 3;
+#define SPB_STAGED(T, R, Q)                                                                 \
+    return collect_staged_t<T, R, Q>(e_total, shift, scale, n_receivers, n_patches, n_alloc, \
+                                     n_bands, n_samples, ld, pad, mono, partial, n_split,    \
+                                     n_stages, st)
+    if (dtype == SPB_F64) {
+        if (shape == 1) SPB_STAGED(double, 16, 4);
+        if (shape == 2) SPB_STAGED(double, 8, 4);
+        if (shape == 3) SPB_STAGED(double, 8, 8);
+    } else {
+        if (shape == 1) SPB_STAGED(float, 16, 4);
+        if (shape == 2) SPB_STAGED(float, 8, 4);
+        if (shape == 3) SPB_STAGED(float, 8, 8);
+    }
+#undef SPB_STAGED
+    return fail(-1, "invalid argument", "shape must be 0 (auto), 1 (16x4), 2 (8x4) or 3 (8x8)");
 }
 
 int spb_collect_patchwise(const void *e_total, const int32_t *rdir, const int32_t *shift,

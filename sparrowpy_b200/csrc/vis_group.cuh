@@ -11,9 +11,16 @@
 //   * otherwise the only members that can block are those whose polygon the plane hit
 //     (or the in-plane end point) can be "in": every other member has
 //     exact::ray_clearance > the distance the member's own hit can differ from the
-//     group's.  The members are binned along the in-plane y axis, so those candidates
-//     are found by scanning one bin; each candidate is then evaluated with the exact
-//     per-blocker predicate exact::blocked.
+//     group's.  The members are listed in a 2-D grid of cells over the in-plane (x, y)
+//     coordinates, so those candidates are found by scanning ONE cell (a handful of
+//     members); each candidate is then evaluated with the exact per-blocker predicate
+//     exact::blocked.  The cell lists hold every member whose expanded bounding box
+//     touches the cell.  That misses the one kind of candidate that lies far from its
+//     polygon: a point LEFT of an axis-aligned rectangle within ~1e-3 of the height of
+//     one of its horizontal edges (its +x ray grazes the edge, see ray_clearance).  The
+//     y-ranges where that can happen ("strips", merged per group) are tabulated; a query
+//     point inside a strip scans the whole 1-D bin along y instead (all members of the
+//     band), as does every query of a group without cells.
 //
 // Whenever a bound needed for these arguments does not hold (end point within the
 // deviation of the eta threshold, grazing segment, huge segment) the group is simply
@@ -34,10 +41,17 @@ struct Group {
     double plane_dev;    // max_k |DOT(S0_k - s0, n)| over the members (0 for lattices)
     double y0;           // lower edge of bin 0 (in-plane y)
     double inv_bin_h;    // 1 / bin height
-    double pad_;
+    double x0;           // left edge of cell column 0 (in-plane x)
+    double inv_bin_w;    // 1 / cell width
     int32_t n_bins;
     int32_t bin_ptr0;    // this group's bins are bin_ptr[bin_ptr0 .. bin_ptr0 + n_bins]
     int32_t m0, m1;      // members[m0 .. m1) = blocker indices of the group
+    int32_t n_bx;        // cell columns (0: no cells, always scan the 1-D bin)
+    int32_t cell_ptr0;   // cell (bx, by) is bin_ptr[cell_ptr0 + by * n_bx + bx .. + 1]
+    int32_t strip0;      // strips[2 * (strip0 + s) + {0, 1}] = [lo, hi] of strip s, sorted
+    int32_t n_strips;
+    int32_t sfirst0;     // bin_ptr[sfirst0 + bin] = first strip with hi >= lower edge of bin
+    int32_t pad_;
 };
 
 constexpr double kGroupMargin = 1e-3;    // how far a member's hit may differ from the group's
@@ -51,16 +65,34 @@ SPB_FN bool group_blocked_bruteforce(const double *A, const double *B, const dou
     return false;
 }
 
+// is qy inside one of the group's strips?  (sorted, disjoint; the scan starts at the first
+// strip that reaches into the query's bin, so it looks at 1-3 strips for a lattice)
+SPB_FN bool in_strip(const Group &g, int32_t bin, double qy, const int32_t *bin_ptr,
+                     const double *strips) {
+    for (int32_t s = bin_ptr[g.sfirst0 + bin]; s < g.n_strips; ++s) {
+        const double lo = strips[2 * (g.strip0 + s)];
+        if (lo > qy) return false;
+        if (qy <= strips[2 * (g.strip0 + s) + 1]) return true;
+    }
+    return false;
+}
+
 // members whose polygon a point within kGroupMargin of (qx, qy) could be "in"
 SPB_FN bool group_blocked_near(const double *A, const double *B, const double *v, double vlen,
                                bool cull_ok, const Group &g, double qx, double qy,
                                const Blocker *blockers, const int32_t *bin_ptr,
-                               const int32_t *bin_items) {
+                               const int32_t *bin_items, const double *strips) {
     const double fb = (qy - g.y0) * g.inv_bin_h;
     if (!(fb > -1.0) || !(fb < (double)g.n_bins + 1.0)) return false;   // outside every band
     int32_t bin = (int32_t)floor(fb);
     bin = bin < 0 ? 0 : (bin >= g.n_bins ? g.n_bins - 1 : bin);
-    const int32_t p0 = bin_ptr[g.bin_ptr0 + bin], p1 = bin_ptr[g.bin_ptr0 + bin + 1];
+    int32_t list = g.bin_ptr0 + bin;                    // 1-D bin: every member of the band
+    if (g.n_bx > 0 && !in_strip(g, bin, qy, bin_ptr, strips)) {
+        const double fx = (qx - g.x0) * g.inv_bin_w;    // NaN -> column 0 (nothing passes)
+        int32_t bx = fx >= 1.0 ? (fx < (double)g.n_bx ? (int32_t)floor(fx) : g.n_bx - 1) : 0;
+        list = g.cell_ptr0 + bin * g.n_bx + bx;
+    }
+    const int32_t p0 = bin_ptr[list], p1 = bin_ptr[list + 1];
     for (int32_t p = p0; p < p1; ++p) {
         const Blocker &k = blockers[bin_items[p]];
         if (ray_clearance(qx, qy, k) > kGroupMargin + kClearGuard) continue;
@@ -73,7 +105,7 @@ SPB_FN bool group_blocked_near(const double *A, const double *B, const double *v
 SPB_FN bool group_blocked(const double *A, const double *B, const double *v, double vlen,
                           bool cull_ok, const Group &g, const Blocker *blockers,
                           const int32_t *members, const int32_t *bin_ptr,
-                          const int32_t *bin_items) {
+                          const int32_t *bin_items, const double *strips) {
     double wa[3], w[3];
     sub3(A, g.s0, wa);
     sub3(B, g.s0, w);
@@ -101,7 +133,7 @@ SPB_FN bool group_blocked(const double *A, const double *B, const double *v, dou
         const double pt[3] = {(w[0] + g.s0[0]) + fac * v[0], (w[1] + g.s0[1]) + fac * v[1],
                               (w[2] + g.s0[2]) + fac * v[2]};
         return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, pt), dot3(g.r1, pt),
-                                  blockers, bin_ptr, bin_items);
+                                  blockers, bin_ptr, bin_items, strips);
     }
     if (inplA && inplB) {
         // both end points in the plane: a member blocks only if an end point is in its
@@ -109,10 +141,10 @@ SPB_FN bool group_blocked(const double *A, const double *B, const double *v, dou
         if (fabs(dp) > 1e-6)
             return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
         if (group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, A), dot3(g.r1, A), blockers,
-                               bin_ptr, bin_items))
+                               bin_ptr, bin_items, strips))
             return true;
         return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, B), dot3(g.r1, B),
-                                  blockers, bin_ptr, bin_items);
+                                  blockers, bin_ptr, bin_items, strips);
     }
     // exactly one end point E in the plane, the other clearly off it: a member blocks
     // only if E is in its polygon, or the plane hit -- within eta*|v|/|dp| of E -- is
@@ -121,14 +153,14 @@ SPB_FN bool group_blocked(const double *A, const double *B, const double *v, dou
         // no plane hit: only "E in the polygon" can block
         const double *E = inplA ? A : B;
         return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, E), dot3(g.r1, E),
-                                  blockers, bin_ptr, bin_items);
+                                  blockers, bin_ptr, bin_items, strips);
     }
     const double slack = (kEta + dev) * vlen / fabs(dp) + 3e-9;
     if (!(slack < kGroupMargin))
         return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
     const double *E = inplA ? A : B;
     return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, E), dot3(g.r1, E), blockers,
-                              bin_ptr, bin_items);
+                              bin_ptr, bin_items, strips);
 }
 
 }  // namespace exact

@@ -519,6 +519,36 @@ def _energy_exchange_batch(tables, e0, delay0, n_samples, max_order):
     return hist
 
 
+STAGED_SHAPES = {1: (16, 4), 2: (8, 4), 3: (8, 8)}    # receivers x bins per thread
+
+
+def collect_kind(hist, n_rcv):
+    """Which collection kernel sums the patches: ``("staged", shape, stages)`` --
+    `k_collect_staged`, every histogram row staged once in shared memory for a group of
+    receivers (diffuse scenes with many receivers, BASELINE config 3) -- or ``("direct",)``,
+    `k_collect_partial` (one row read per receiver).  ``SPB_COLLECT=direct`` or
+    ``staged[:shape[:stages]]`` forces one (cross-check tests, tools/sweep_collect.py)."""
+    env = os.environ.get("SPB_COLLECT", "").split(":")
+    esize = hist.data.element_size()
+    shape = 3 if hist.n_samples > 1024 else (1 if n_rcv > 8 else 2)
+    stages = 0
+    if env[0] == "staged":
+        shape = int(env[1]) if len(env) > 1 else shape
+        stages = int(env[2]) if len(env) > 2 else 0
+    n_r, n_q = STAGED_SHAPES[shape]
+    vec = 16 // esize
+    row2 = -(-hist.n_samples // vec) * vec + -(-hist.n_samples // (256 * n_q)) * 256 * n_q
+    fits = hist.n_dirs == 1 and max(2, stages) * ((row2 + n_r) * esize + 4 * n_r) <= 220 * 1024
+    if env[0] == "staged":
+        if not fits:
+            raise _lib.SparrowB200Error("SPB_COLLECT=staged needs one direction per patch and "
+                                        "histogram rows that fit shared memory")
+        return ("staged", shape, stages)
+    if env[0] == "direct" or not fits or n_rcv < 4:
+        return ("direct",)
+    return ("staged", shape, stages)
+
+
 def collect_mono(hist, rdir, shift, scale, n_split=None):
     """Sum of all patch histograms at each receiver, (R, B, T)
     (``collect_energy_receiver_mono``, RadiosityFast.py:570-602 / :1148-1185).
@@ -535,12 +565,20 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
         n_split = max(1, min(64, hist.n_patches // 256))
     out = torch.empty((n_rcv, hist.n_bands, hist.n_samples), dtype=tdt,
                       device=hist.data.device)
+    kind = collect_kind(hist, n_rcv)
     # grid.y carries receiver*band: batch the receivers if there are many
     step = max(1, 65535 // hist.n_bands)
     for r0 in range(0, n_rcv, step):
         r1 = min(n_rcv, r0 + step)
         partial = torch.empty((n_split, r1 - r0, hist.n_bands, hist.n_samples), dtype=tdt,
                               device=hist.data.device)
+        if kind[0] == "staged":
+            _lib.call("spb_collect_mono_staged", hist.data, shift[r0:r1].contiguous(),
+                      scale[r0:r1].to(tdt).contiguous(), r1 - r0, hist.n_patches, hist.n_alloc,
+                      hist.n_bands, hist.n_samples, hist.ld, hist.pad, out[r0:r1], partial,
+                      n_split, _lib.I32(kind[1]), _lib.I32(kind[2]), _lib.I32(code),
+                      _lib.stream_ptr())
+            continue
         _lib.call("spb_collect_mono", hist.data, rdir[r0:r1].contiguous(),
                   shift[r0:r1].contiguous(), scale[r0:r1].to(tdt).contiguous(), r1 - r0,
                   hist.n_patches, hist.n_alloc, hist.n_dirs, hist.n_bands, hist.n_samples,

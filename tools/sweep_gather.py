@@ -4,11 +4,10 @@ bakes once, then for every kernel variant builds its tables, runs a few reflecti
 orders, times the gather launches with CUDA events and checks the histogram against
 the default kernel.
 
-    python tools/sweep_gather.py --config c4 [--orders 3] [--variants tma,win,win-v2,...]
+    python tools/sweep_gather.py --config c4 [--orders 3] [--variants tma,tmem,tmem@natural]
 
-Variants: tma | tmem | csr | win (variant 1) | win-lt4 | win-v2 | win-v3, each optionally with
-`@a4` = sector-aligned rows (SPB_WIN_ALIGN=4), e.g. `win-v3@a4`.  Unverified variants
-are run in this process: wrap the call in `timeout`."""
+Variants: tma | tmem | csr, each optionally with `@<order>` = launch order of the tiles
+(SPB_TILE_ORDER: lpt, natural, window<W>), e.g. `tmem@window1184`."""
 import argparse
 import os
 import sys
@@ -21,19 +20,15 @@ ENV = {
     "tma": dict(SPB_GATHER="tma"),
     "tmem": dict(SPB_GATHER="tmem"),
     "csr": dict(SPB_GATHER="csr"),
-    "win": dict(SPB_GATHER="win"),
-    "win-lt4": dict(SPB_GATHER="win", SPB_WIN_LANE_T="4"),
-    "win-v2": dict(SPB_GATHER="win", SPB_WIN_VARIANT="2"),
-    "win-v3": dict(SPB_GATHER="win", SPB_WIN_VARIANT="3"),
 }
-KEYS = ("SPB_GATHER", "SPB_WIN_LANE_T", "SPB_WIN_VARIANT", "SPB_WIN_ALIGN")
+KEYS = ("SPB_GATHER", "SPB_TILE_ORDER")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c4")
     ap.add_argument("--orders", type=int, default=3)
-    ap.add_argument("--variants", default="tma,tmem,win-v3")
+    ap.add_argument("--variants", default="tma,tmem,tmem@natural")
     args = ap.parse_args()
     import torch
     import bench
@@ -51,8 +46,8 @@ def main():
         for k in KEYS:
             os.environ.pop(k, None)
         os.environ.update(ENV[base])
-        if opt == "a4":
-            os.environ["SPB_WIN_ALIGN"] = "4"
+        if opt:
+            os.environ["SPB_TILE_ORDER"] = opt
         rad._tables = None                         # tables depend on the kernel
         t0 = time.time()
         tables = rad._pair_tables(bench.SPEED_OF_SOUND, bench.DT, n_samples)

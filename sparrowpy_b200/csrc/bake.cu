@@ -200,10 +200,9 @@ k_vis_pt2p(const double *__restrict__ points, const double *__restrict__ centers
 // (vis_group.cuh); the group headers are staged in shared memory when they fit
 constexpr int kMaxGroupsSmem = 128;
 
-// kMinBlocks: resident CTAs per SM the register allocation is bounded for (3: no spills;
-// 4: 128 registers, a few spills -- SPB_VIS_MINBLOCKS=4, tools/sweep_vis.py)
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kVisThreads, kMinBlocks)
+// 4 resident CTAs per SM (128 registers, 268 bytes of spills): measured 79.4 ms against
+// 92.3 ms with the 167 registers ptxas takes unbounded (C4, profiles/r02_sweep_vis_c4.jsonl)
+__global__ void __launch_bounds__(kVisThreads, 4)
 k_vis_p2p_grouped(const double *__restrict__ centers, int64_t n,
                   const Blocker *__restrict__ blockers, const exact::Group *__restrict__ groups,
                   int32_t n_groups, const int32_t *__restrict__ members,
@@ -261,50 +260,6 @@ __device__ __forceinline__ void boundary_point(const double *el, int idx, int n_
 __device__ __forceinline__ double boole(double x0, double x1, const double *y) {
     const double h = x1 - x0;                                       // integration.py:481-486
     return 2 * h / 45 * (7 * y[0] + 32 * y[1] + 12 * y[2] + 32 * y[3] + 7 * y[4]);
-}
-
-// integration.py:38-114
-__device__ double stokes_integration(const double *pi, const double *pj, double area_i) {
-    double inner[16][3];
-    double outer = 0.0;
-    for (int a = 0; a < 16; ++a) {
-        double pa[3];
-        boundary_point(pi, a, 4, pa);
-        double y[17];                                   // log|p_a - q_b|, b = 0..15, 0
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-            double q[3], d[3];
-            boundary_point(pj, b, 4, q);
-            exact::sub3(pa, q, d);
-            y[b] = log(nrm3p(d));
-        }
-        y[16] = y[0];
-        for (int dim = 0; dim < 3; ++dim) {
-            double acc = 0.0;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const double x0 = pj[3 * s + dim];
-                const double xl = pj[3 * ((s + 1) & 3) + dim];
-                if (fabs(xl - x0) > 1e-3) {
-                    const double x1 = x0 + 1.0 * (xl - x0) / 4.0;
-                    acc += boole(x0, x1, y + 4 * s);
-                }
-            }
-            inner[a][dim] = acc;
-        }
-    }
-    for (int dim = 0; dim < 3; ++dim)
-        for (int s = 0; s < 4; ++s) {
-            const double x0 = pi[3 * s + dim];
-            const double xl = pi[3 * ((s + 1) & 3) + dim];
-            if (fabs(xl - x0) > 1e-3) {
-                const double x1 = x0 + 1.0 * (xl - x0) / 4.0;
-                double y[5];
-                for (int k = 0; k < 5; ++k) y[k] = inner[(4 * s + k) & 15][dim];
-                outer += boole(x0, x1, y);
-            }
-        }
-    return fabs(outer / (2 * SPB_PI * area_i));
 }
 
 __device__ __forceinline__ double sgn(double v) { return (double)((v > 0) - (v < 0)); }
@@ -388,33 +343,83 @@ __device__ double nusselt_analog(const double *o, const double *R /*rot(n_i)*/,
     return big + hand * curved;
 }
 
-// geometry.py:719-748 (vertices coincide exactly or are a patch size apart)
-__device__ __forceinline__ bool coincidence_check(const double *p0, const double *p1) {
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-            double d[3];
-            exact::sub3(p0 + 3 * i, p1 + 3 * j, d);
-            if (nrm3p(d) < 1e-6) return true;
-        }
-    return false;
-}
-
-// universal.py:12-96, Stokes branch; Nusselt pairs are flagged for the warp kernel
-__global__ void __launch_bounds__(128)
+// universal.py:12-96, Stokes branch (integration.py:38-114); Nusselt pairs are flagged for
+// the warp kernel.  16 lanes per pair (two pairs per warp): lane a owns boundary point a of
+// patch i -- its 16 logarithms log|p_a - q_b| and the three inner Boole sums over the
+// boundary of patch j -- and the outer Boole sum over the boundary of patch i is a weighted
+// shuffle reduction over the 16 lanes (a point at a corner closes one segment and opens the
+// next: weight 7 in both).  No per-thread tables, no local memory.
+__global__ void __launch_bounds__(128, 4)
 k_ff_stokes(const double *__restrict__ pts, const double *__restrict__ areas,
             const int32_t *__restrict__ pairs, int64_t n_pairs, double *__restrict__ ff,
             uint8_t *__restrict__ nusselt_flag) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = threadIdx.x & 15;
+    const unsigned half_mask = 0xffffu << (threadIdx.x & 16);
+    const bool live = (gid >> 4) < n_pairs;
+    const int64_t p = live ? (gid >> 4) : n_pairs - 1;     // idle lanes shadow the last pair
     const int64_t i = pairs[2 * p], j = pairs[2 * p + 1];
-    double pi[12], pj[12];
-    for (int k = 0; k < 12; ++k) { pi[k] = pts[12 * i + k]; pj[k] = pts[12 * j + k]; }
-    if (coincidence_check(pj, pi)) {
-        nusselt_flag[p] = 1;
+    double pj[12];
+    for (int k = 0; k < 12; ++k) pj[k] = pts[12 * j + k];
+    // geometry.py:719-748: lane a compares vertex a / 4 of patch j with vertex a % 4 of patch i
+    // (dynamic vertex indices address global memory, the register copies stay statically indexed)
+    double dv[3];
+    exact::sub3(pts + 12 * j + 3 * (a >> 2), pts + 12 * i + 3 * (a & 3), dv);
+    const bool touch = __any_sync(half_mask, nrm3p(dv) < 1e-6);
+    if (touch) {
+        if (a == 0 && live) nusselt_flag[p] = 1;
         return;
     }
-    nusselt_flag[p] = 0;
-    ff[p] = stokes_integration(pi, pj, areas[i]);
+    double pa[3];
+    boundary_point(pts + 12 * i, a, 4, pa);
+    // Boole coefficient 2 h / 45 of segment s of a boundary in coordinate dim (0 where the
+    // segment does not move in that coordinate, integration.py:86-95)
+    auto seg_coef = [](const double *el, int s, int dim) {
+        const double x0 = el[3 * s + dim], xl = el[3 * ((s + 1) & 3) + dim];
+        return fabs(xl - x0) > 1e-3 ? 2 * ((x0 + 1.0 * (xl - x0) / 4.0) - x0) / 45 : 0.0;
+    };
+    double cj[4][3];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int dim = 0; dim < 3; ++dim) cj[s][dim] = seg_coef(pj, s, dim);
+    // inner sums over the boundary of patch j, accumulated as the logarithms arrive: point b
+    // is sample b % 4 of segment b / 4 and, at a corner, also sample 4 of the segment before
+    double inner[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        double q[3], d[3];
+        boundary_point(pj, b, 4, q);
+        exact::sub3(pa, q, d);
+        const double yb = log(nrm3p(d));                // log|p_a - q_b|
+        const int s = b >> 2, k = b & 3;
+        const double w = k == 0 ? 7.0 : (k == 2 ? 12.0 : 32.0);
+#pragma unroll
+        for (int dim = 0; dim < 3; ++dim) {
+            double c = w * cj[s][dim];
+            if (k == 0) c += 7.0 * cj[(s + 3) & 3][dim];
+            inner[dim] += c * yb;
+        }
+    }
+    // this lane's weight in the outer sum over the boundary of patch i: the same rule with a
+    // (dynamic segment index: read from global memory)
+    double contrib = 0.0;
+    {
+        const double *gi = pts + 12 * i;
+        const int s = a >> 2, k = a & 3;
+        const double w = k == 0 ? 7.0 : (k == 2 ? 12.0 : 32.0);
+#pragma unroll
+        for (int dim = 0; dim < 3; ++dim) {
+            double c = w * seg_coef(gi, s, dim);
+            if (k == 0) c += 7.0 * seg_coef(gi, (s + 3) & 3, dim);
+            contrib += c * inner[dim];
+        }
+    }
+    for (int off = 8; off > 0; off >>= 1) contrib += __shfl_xor_sync(half_mask, contrib, off);
+    if (a == 0 && live) {
+        nusselt_flag[p] = 0;
+        ff[p] = fabs(contrib / (2 * SPB_PI * areas[i]));
+    }
 }
 
 // integration.py:232-289 with :533-605: one warp per flagged pair, lanes over the
@@ -660,15 +665,9 @@ static int launch_vis_grouped(unsigned grid, cudaStream_t st, const double *cent
                               const int32_t *members, const int32_t *bin_ptr,
                               const int32_t *bin_items, const double *strips, int64_t chunks,
                               int64_t row_lo, uint8_t *vis) {
-    const char *env = getenv("SPB_VIS_MINBLOCKS");
-    if (env && env[0] == '4')
-        k_vis_p2p_grouped<4><<<grid, kVisThreads, 0, st>>>(
-            centers, n, (const Blocker *)blockers, (const exact::Group *)groups,
-            (int32_t)n_groups, members, bin_ptr, bin_items, strips, chunks, row_lo, vis);
-    else
-        k_vis_p2p_grouped<3><<<grid, kVisThreads, 0, st>>>(
-            centers, n, (const Blocker *)blockers, (const exact::Group *)groups,
-            (int32_t)n_groups, members, bin_ptr, bin_items, strips, chunks, row_lo, vis);
+    k_vis_p2p_grouped<<<grid, kVisThreads, 0, st>>>(
+        centers, n, (const Blocker *)blockers, (const exact::Group *)groups, (int32_t)n_groups,
+        members, bin_ptr, bin_items, strips, chunks, row_lo, vis);
     return check_launch("k_vis_p2p_grouped");
 }
 
@@ -794,7 +793,8 @@ int spb_form_factors_stokes(const double *pts, const double *areas, const int32_
                             int64_t n_pairs, double *ff, uint8_t *nusselt_flag, void *stream) {
     SPB_REQUIRE(pts && areas && ff && nusselt_flag && (pairs || n_pairs == 0), "null pointer");
     if (n_pairs == 0) return 0;
-    k_ff_stokes<<<(unsigned)ceil_div(n_pairs, 128), 128, 0, (cudaStream_t)stream>>>(
+    SPB_REQUIRE(n_pairs <= (2147483647LL * 8), "too many pairs for one launch");
+    k_ff_stokes<<<(unsigned)ceil_div(n_pairs * 16, 128), 128, 0, (cudaStream_t)stream>>>(
         pts, areas, pairs, n_pairs, ff, nusselt_flag);
     return check_launch("k_ff_stokes");
 }

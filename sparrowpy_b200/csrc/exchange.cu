@@ -280,37 +280,40 @@ k_collect_staged(const T *__restrict__ e_total, const int32_t *__restrict__ shif
     const uint32_t smem0 = smem_addr(smem_raw);
     // bins past copy B are read by tail threads only (t >= n_samples, never stored); zero them
     // once so that no stale bit pattern is ever multiplied (the pieces of copy B may spill
-    // kVec - 1 elements into this zone: finite values of the row's padding)
+    // kVec - 1 elements into this zone: finite values of the row's padding).  Scale and shift
+    // slots of receivers past the last one stay zero for the whole kernel.
     for (int s = 0; s < n_stages; ++s) {
         T *row = reinterpret_cast<T *>(smem_raw + (size_t)s * stage_bytes);
         for (int i = 2 * t_al + tid; i < row2; i += 256) row[i] = T(0);
+        if (tid < kRcv) {
+            row[row2 + tid] = T(0);
+            reinterpret_cast<int32_t *>(row + row2 + kRcv)[tid] = 0;
+        }
     }
+    __syncthreads();
+    // the receiver factors of this thread's receiver (threads < kRcv): everything in the loop
+    // is asynchronous -- a synchronous global load here would stall the whole CTA at the next
+    // barrier for a DRAM latency per patch
+    const bool has_rcv = tid < kRcv && r0 + tid < n_receivers;
+    const T *my_scale = scale + ((int64_t)(r0 + (has_rcv ? tid : 0)) * n_patches + k_lo) * n_bands + b;
+    const int32_t *my_shift = shift + (int64_t)(r0 + (has_rcv ? tid : 0)) * n_patches + k_lo;
+    const T *band_rows = e_total + ((int64_t)b * n_alloc + k_lo) * ld + pad;
 
-    auto issue = [&](int i) {                  // patch k_lo + i -> stage i % n_stages
-        const int so = (i % n_stages) * stage_bytes;
-        const int64_t k = k_lo + i;
-        const T *src = e_total + ((int64_t)b * n_alloc + k) * ld + pad;
+    auto issue = [&](int i, int stage) {       // patch k_lo + i -> stage
+        const uint32_t so = smem0 + stage * stage_bytes;
+        const T *src = band_rows + (int64_t)i * ld;
         for (int v = tid; v < n_vec; v += 256) {
-            cp_async_16(smem0 + so + (t_al + v * kVec) * (int)sizeof(T), src + (size_t)v * kVec);
-            if (aligned) cp_async_16(smem0 + so + v * 16, src + (size_t)v * kVec);
+            cp_async_16(so + (t_al + v * kVec) * (int)sizeof(T), src + (size_t)v * kVec);
+            if (aligned) cp_async_16(so + v * 16, src + (size_t)v * kVec);
         }
         if (!aligned)                           // copy A element by element
             for (int v = tid; v < n_samples; v += 256)
-                cp_async_small<(int)sizeof(T)>(
-                    smem0 + so + (t_al - n_samples + v) * (int)sizeof(T), src + v);
-        if (tid < kRcv) {
-            T *sc = reinterpret_cast<T *>(smem_raw + so + (size_t)row2 * sizeof(T));
-            int32_t *off = reinterpret_cast<int32_t *>(sc + kRcv);
-            const int r = r0 + tid;
-            T c = T(0);
-            int32_t h = 0;
-            if (r < n_receivers) {
-                const int64_t rk = (int64_t)r * n_patches + k;
-                c = scale[rk * n_bands + b];
-                h = shift[rk];                 // 0 <= h < n_samples
-            }
-            sc[tid] = c;                       // plain stores, published by the __syncthreads
-            off[tid] = (t_al - h) * (int)sizeof(T);   // that precedes the stage's first read
+                cp_async_small<(int)sizeof(T)>(so + (t_al - n_samples + v) * (int)sizeof(T),
+                                               src + v);
+        if (has_rcv) {
+            cp_async_small<(int)sizeof(T)>(so + (row2 + tid) * (int)sizeof(T),
+                                           my_scale + (int64_t)i * n_bands);
+            cp_async_small<4>(so + (row2 + kRcv) * (int)sizeof(T) + tid * 4, my_shift + i);
         }
     };
 
@@ -321,20 +324,23 @@ k_collect_staged(const T *__restrict__ e_total, const int32_t *__restrict__ shif
         for (int q = 0; q < kBins; ++q) acc[r][q] = T(0);
 
     for (int i = 0; i < n_stages - 1; ++i) {
-        if (i < n_k) issue(i);
+        if (i < n_k) issue(i, i);
         cp_async_commit();
     }
+    int stage = 0;                             // stage of patch i
+    int refill = n_stages - 1;                 // stage of patch i + n_stages - 1 (= of patch i-1)
+    const int sh_scale = (int)sizeof(T);
     for (int i = 0; i < n_k; ++i) {
         cp_async_wait_pending(n_stages - 2);   // the copies of patch i have landed
         __syncthreads();                       // ... for every thread; patch i-1 is consumed
-        if (i + n_stages - 1 < n_k) issue(i + n_stages - 1);   // refills the stage of patch i-1
+        if (i + n_stages - 1 < n_k) issue(i + n_stages - 1, refill);
         cp_async_commit();
-        const unsigned char *st = smem_raw + (size_t)(i % n_stages) * stage_bytes;
-        const unsigned char *mine = st + (size_t)t0 * sizeof(T);
+        const unsigned char *st = smem_raw + (size_t)stage * stage_bytes;
+        const unsigned char *mine = st + (size_t)(t0 + t_al) * sizeof(T);
         const T *sc = reinterpret_cast<const T *>(st) + row2;
-        const int4 *off4 = reinterpret_cast<const int4 *>(sc + kRcv);
+        const int4 *sh4 = reinterpret_cast<const int4 *>(sc + kRcv);
         T c[kRcv];
-        int off[kRcv];
+        int sh[kRcv];
 #pragma unroll
         for (int r = 0; r < kRcv; r += kVec) {
             const int4 raw = *reinterpret_cast<const int4 *>(sc + r);   // kVec scales
@@ -344,15 +350,18 @@ k_collect_staged(const T *__restrict__ e_total, const int32_t *__restrict__ shif
         }
 #pragma unroll
         for (int r = 0; r < kRcv; r += 4) {
-            const int4 o = off4[r / 4];
-            off[r] = o.x; off[r + 1] = o.y; off[r + 2] = o.z; off[r + 3] = o.w;
+            const int4 o = sh4[r / 4];
+            sh[r] = o.x; sh[r + 1] = o.y; sh[r + 2] = o.z; sh[r + 3] = o.w;
         }
 #pragma unroll
         for (int r = 0; r < kRcv; ++r) {
-            const T *win = reinterpret_cast<const T *>(mine + off[r]);
+            // row2[t_al - shift + t]: copy B for t >= shift, copy A (the wrapped bins) below
+            const T *win = reinterpret_cast<const T *>(mine - sh[r] * sh_scale);
 #pragma unroll
             for (int q = 0; q < kBins; ++q) acc[r][q] += win[256 * q] * c[r];
         }
+        stage = stage + 1 == n_stages ? 0 : stage + 1;
+        refill = refill + 1 == n_stages ? 0 : refill + 1;
     }
     cp_async_wait_pending(0);
 #pragma unroll

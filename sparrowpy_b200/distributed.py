@@ -161,16 +161,13 @@ class ShardedExchange:
 
     def cta_order(self, j_lo=None, j_hi=None):
         """Launch order of the tiles of receivers [j_lo, j_hi) (default: the shard): longest
-        record lists first (LPT), so the short tiles fill the tail of the grid.
-        ``SPB_TILE_ORDER`` (experiments, tools/sweep_gather.py): ``natural`` = class-major,
-        neighbouring receivers next to each other (concurrent CTAs then walk the same sender
-        rows: L2 locality instead of balance), ``window<W>`` = natural order with LPT inside
-        consecutive windows of W tiles."""
+        record lists first (LPT), so the short tiles fill the tail of the grid.  (A class-major
+        "neighbouring receivers together" order for L2 locality was measured on C2 and makes no
+        difference: 13.5 ms either way, profiles/r02_tile_order_c2.txt.)"""
         j_lo = self.j_lo if j_lo is None else j_lo
         j_hi = self.j_hi if j_hi is None else j_hi
-        mode = os.environ.get("SPB_TILE_ORDER", "lpt")
         cache = self.__dict__.setdefault("_cta_orders", {})
-        if (j_lo, j_hi, mode) not in cache:
+        if (j_lo, j_hi) not in cache:
             t = self.t
             n_r = SHARD_ALIGN
             n_blocks = -(-t.n_patches // n_r)
@@ -178,20 +175,9 @@ class ShardedExchange:
             ptr = t.tile_ptr
             counts = (ptr[1:] - ptr[:-1]).view(t.n_classes, n_blocks)
             local = counts[:, jb_lo:jb_hi].reshape(-1)
-            if mode == "lpt":
-                order = torch.argsort(local, descending=True, stable=True)
-            elif mode == "natural":
-                order = torch.arange(local.numel(), device=local.device)
-            elif mode.startswith("window"):
-                w = int(mode[len("window"):])
-                win = torch.arange(local.numel(), device=local.device) // w
-                # sort by (window ascending, length descending)
-                key = win * (int(local.max().item()) + 1) + (int(local.max().item()) - local)
-                order = torch.argsort(key, stable=True)
-            else:
-                raise ValueError(f"SPB_TILE_ORDER={mode!r}: use lpt, natural or window<W>")
-            cache[(j_lo, j_hi, mode)] = order.to(torch.int32).contiguous()
-        return cache[(j_lo, j_hi, mode)]
+            cache[(j_lo, j_hi)] = torch.argsort(local, descending=True, stable=True).to(
+                torch.int32).contiguous()
+        return cache[(j_lo, j_hi)]
 
     def _mix(self, cur, total, b_lo, b_hi, j_lo=None, j_hi=None):
         """Stage 2; with symmetric buffers it also delivers E_k to every rank."""

@@ -561,11 +561,15 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
     rdir, shift, scale = (hist.to_internal(x, 1) for x in (rdir, shift, scale))
     if hist.n_sources is not None:          # the same receiver factors for every source
         scale = scale.repeat(1, 1, hist.n_sources)
+    kind = collect_kind(hist, n_rcv)
     if n_split is None:
         n_split = max(1, min(64, hist.n_patches // 256))
+        if kind[0] == "staged":             # ~8 waves of CTAs (2 per SM), >= 64 patches each
+            n_r, n_q = STAGED_SHAPES[kind[1]]
+            ctas = hist.n_bands * -(-n_rcv // n_r) * -(-hist.n_samples // (256 * n_q))
+            n_split = max(1, min(hist.n_patches // 64, -(-8 * 2 * 148 // ctas)))
     out = torch.empty((n_rcv, hist.n_bands, hist.n_samples), dtype=tdt,
                       device=hist.data.device)
-    kind = collect_kind(hist, n_rcv)
     # grid.y carries receiver*band: batch the receivers if there are many
     step = max(1, 65535 // hist.n_bands)
     for r0 in range(0, n_rcv, step):

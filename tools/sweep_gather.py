@@ -4,10 +4,7 @@ bakes once, then for every kernel variant builds its tables, runs a few reflecti
 orders, times the gather launches with CUDA events and checks the histogram against
 the default kernel.
 
-    python tools/sweep_gather.py --config c4 [--orders 3] [--variants tma,tmem,tmem@natural]
-
-Variants: tma | tmem | csr, each optionally with `@<order>` = launch order of the tiles
-(SPB_TILE_ORDER: lpt, natural, window<W>), e.g. `tmem@window1184`."""
+    python tools/sweep_gather.py --config c4 [--orders 3] [--variants tma,tmem,csr]"""
 import argparse
 import os
 import sys
@@ -21,14 +18,14 @@ ENV = {
     "tmem": dict(SPB_GATHER="tmem"),
     "csr": dict(SPB_GATHER="csr"),
 }
-KEYS = ("SPB_GATHER", "SPB_TILE_ORDER")
+KEYS = ("SPB_GATHER",)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c4")
     ap.add_argument("--orders", type=int, default=3)
-    ap.add_argument("--variants", default="tma,tmem,tmem@natural")
+    ap.add_argument("--variants", default="tma,tmem")
     args = ap.parse_args()
     import torch
     import bench
@@ -42,12 +39,10 @@ def main():
     ref = None
     print(f"{args.config}: N={rad.n_patches} pairs={rad._baked['pairs'].shape[0]}", flush=True)
     for name in args.variants.split(","):
-        base, _, opt = name.partition("@")
+        base = name
         for k in KEYS:
             os.environ.pop(k, None)
         os.environ.update(ENV[base])
-        if opt:
-            os.environ["SPB_TILE_ORDER"] = opt
         rad._tables = None                         # tables depend on the kernel
         t0 = time.time()
         tables = rad._pair_tables(bench.SPEED_OF_SOUND, bench.DT, n_samples)

@@ -1,6 +1,6 @@
 """Time the hierarchical visibility kernel on a bench scene: 2-D cells on / off (cells off =
-every candidate scan walks the whole y-bin, the round-1/2a behaviour) and the two register
-bounds of the kernel; all matrices must be identical.
+every candidate scan walks the whole y-bin, the behaviour before the cells); the matrices
+must be identical.
 
     python tools/sweep_vis.py --config c4"""
 import argparse
@@ -31,9 +31,7 @@ def main():
     off = tabs[0].copy()
     off.view(np.int32).reshape(len(off), -1)[:, bake._GRP_I["n_bx"]] = 0
     ref = None
-    for name, groups, minblocks in (("cells", tabs[0], "3"), ("cells", tabs[0], "4"),
-                                    ("bins only", off, "3")):
-        os.environ["SPB_VIS_MINBLOCKS"] = minblocks
+    for name, groups in (("cells", tabs[0]), ("bins only", off)):
         dv = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (groups,) + tabs[1:]]
         vis = torch.empty((n, n), dtype=torch.uint8, device=dev)
         ms = []
@@ -48,7 +46,7 @@ def main():
         if ref is None:
             ref = vis.clone()
         print(json.dumps({"config": args.config, "n_patches": n, "tables": name,
-                          "min_blocks": int(minblocks), "ms": [round(x, 2) for x in ms],
+                          "ms": [round(x, 2) for x in ms],
                           "visible_pairs": int(vis.sum().item()),
                           "equals_first": bool(torch.equal(vis, ref))}), flush=True)
 

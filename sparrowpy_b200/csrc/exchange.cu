@@ -732,7 +732,7 @@ int spb_collect_mono_staged(const void *e_total, const int32_t *shift, const voi
     SPB_REQUIRE(dtype == SPB_F64 || dtype == SPB_F32, "dtype");
     if (n_receivers == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (shape == 0) shape = n_samples <= 1024 ? 1 : 3;
+    if (shape == 0) shape = 2;
 #define SPB_STAGED(T, R, Q)                                                                 \
     return collect_staged_t<T, R, Q>(e_total, shift, scale, n_receivers, n_patches, n_alloc, \
                                      n_bands, n_samples, ld, pad, mono, partial, n_split,    \

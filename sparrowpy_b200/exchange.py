@@ -530,7 +530,7 @@ def collect_kind(hist, n_rcv):
     ``staged[:shape[:stages]]`` forces one (cross-check tests, tools/sweep_collect.py)."""
     env = os.environ.get("SPB_COLLECT", "").split(":")
     esize = hist.data.element_size()
-    shape = 3 if hist.n_samples > 1024 else (1 if n_rcv > 8 else 2)
+    shape = 2           # 8 receivers x 4 bins, 2 CTAs per SM: fastest at T = 1000 and 2000
     stages = 0
     if env[0] == "staged":
         shape = int(env[1]) if len(env) > 1 else shape

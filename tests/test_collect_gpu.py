@@ -75,11 +75,11 @@ def test_default_kernel_choice(monkeypatch):
     from sparrowpy_b200 import exchange
     monkeypatch.delenv("SPB_COLLECT", raising=False)
     hist, *_ = make_case(1, 4, 1, 1000, torch.float64)
-    assert exchange.collect_kind(hist, 64)[:2] == ("staged", 1)
-    assert exchange.collect_kind(hist, 8)[:2] == ("staged", 2)
+    assert exchange.collect_kind(hist, 64)[:2] == ("staged", 2)
+    assert exchange.collect_kind(hist, 4)[:2] == ("staged", 2)
     assert exchange.collect_kind(hist, 3) == ("direct",)
     hist.n_samples = 2000
-    assert exchange.collect_kind(hist, 64)[:2] == ("staged", 3)
+    assert exchange.collect_kind(hist, 64)[:2] == ("staged", 2)
     hist.n_samples = 40000
     assert exchange.collect_kind(hist, 64) == ("direct",)
     hist.n_samples, hist.n_dirs = 1000, 4

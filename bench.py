@@ -247,15 +247,20 @@ def time_bake(rad, n_pairs):
                                      _lib.stream_ptr()), reps=1)
     # hierarchical variant (the one bake_geometry uses): tables built once, kernel timed
     import numpy as _np
-    groups, members, bin_ptr, bin_items, strips = bake.build_groups(
+    groups, members, bin_ptr, bin_items, strips, group_of = bake.build_groups(
         blockers.cpu().numpy().reshape(n, -1), rad._patch_to_wall_ids)
     dev = g["center"].device
-    gt, mt, bp, bi, sp = (torch.from_numpy(_np.ascontiguousarray(a)).to(dev)
-                          for a in (groups, members, bin_ptr, bin_items, strips))
+    gt, mt, bp, bi, sp, og = (torch.from_numpy(_np.ascontiguousarray(a)).to(dev)
+                              for a in (groups, members, bin_ptr, bin_items, strips, group_of))
+    own_in = torch.empty(n, dtype=torch.uint8, device=dev)
     vis_g = torch.empty_like(vis)
-    vis_grouped_ms = timed(lambda: _lib.call(
-        "spb_visibility_p2p_grouped", g["center"], n, blockers, gt, len(groups), mt, bp, bi, sp,
-        vis_g, _lib.stream_ptr()), reps=1)
+
+    def grouped():
+        _lib.call("spb_visibility_own_in", g["center"], n, blockers, own_in, _lib.stream_ptr())
+        _lib.call("spb_visibility_p2p_grouped", g["center"], n, blockers, gt, len(groups), mt,
+                  bp, bi, sp, own_in, og, vis_g, _lib.stream_ptr())
+
+    vis_grouped_ms = timed(grouped, reps=1)
     same = bool(torch.equal(vis, vis_g))
     pairs = rad._baked["pairs"]
     ff_ms = timed(lambda: bake.form_factors(g["points"], g["normal"], g["area"], pairs))

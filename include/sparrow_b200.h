@@ -266,18 +266,27 @@ int spb_visibility_p2p(const double *centers, int64_t n, const void *blockers, i
  * are evaluated individually.  O(N^2 * walls) instead of O(N^3).  Tables from
  * sparrowpy_b200.bake.build_groups: groups: n_groups records of spb_group_bytes() bytes;
  * members: blocker indices; bin_ptr / bin_items: CSR of the y-bins and cells of all groups
- * (+ the per-bin first-strip index); strips: [lo, hi] pairs of the grazing y-ranges. */
+ * (+ the per-bin first-strip index); strips: [lo, hi] pairs of the grazing y-ranges.
+ * Two optional (nullable) accelerators that cannot change the result: own_in[i] (uint8, N,
+ * from spb_visibility_own_in; 255 = unknown) = "centre i lies in polygon i", the one exact
+ * polygon test nearly every pair repeats, memoised per patch; own_group[i] (int32, N; -1 =
+ * none) = the group of blocker i, evaluated first for the pairs of patch i (the conjunction
+ * over the blockers is order-independent, geometry.py:786-795). */
+int spb_visibility_own_in(const double *centers, int64_t count, const void *blockers,
+                          uint8_t *own_in, void *stream);
 size_t spb_group_bytes(void);
 int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blockers,
                                const void *groups, int64_t n_groups, const int32_t *members,
                                const int32_t *bin_ptr, const int32_t *bin_items,
-                               const double *strips, uint8_t *vis, void *stream);
+                               const double *strips, const uint8_t *own_in,
+                               const int32_t *own_group, uint8_t *vis, void *stream);
 /* Rows [row_lo, row_hi) of the same matrix into vis_rows ([row_hi - row_lo, N] uint8): the
  * unit of the bake when it is sharded over GPUs (pair tiles are independent). */
 int spb_visibility_p2p_grouped_rows(const double *centers, int64_t n, const void *blockers,
                                     const void *groups, int64_t n_groups,
                                     const int32_t *members, const int32_t *bin_ptr,
                                     const int32_t *bin_items, const double *strips,
+                                    const uint8_t *own_in, const int32_t *own_group,
                                     int64_t row_lo, int64_t row_hi, uint8_t *vis_rows,
                                     void *stream);
 /* host twins of spb_make_blockers / spb_visibility_p2p_grouped (HOST pointers): the
@@ -288,7 +297,7 @@ int spb_visibility_p2p_grouped_host(const double *centers_h, int64_t n, const vo
                                     const void *groups_h, int64_t n_groups,
                                     const int32_t *members_h, const int32_t *bin_ptr_h,
                                     const int32_t *bin_items_h, const double *strips_h,
-                                    uint8_t *vis_h);
+                                    int64_t n_own, const int32_t *own_group_h, uint8_t *vis_h);
 
 /* `_check_point2patch_visibility` (geometry.py:799-839) for a batch of points:
  * vis[r,j] ([R,N] uint8). */

@@ -250,7 +250,8 @@ def build_groups(blockers_np, group_ids):
     expanded bounding box touches the cell, plus the y-ranges ("strips") in which a point far
     to the left of an axis-aligned member can still be a candidate (the kernel then scans the
     bin instead of the cell).  Returns numpy arrays (groups uint8 (G, group_bytes), members
-    int32, bin_ptr int32, bin_items int32, strips float64 (n, 2)).
+    int32, bin_ptr int32, bin_items int32, strips float64 (n, 2), group_of int32 (M,) = the
+    group of every blocker).
     """
     import numpy as np
     lib = _lib.load()
@@ -369,9 +370,12 @@ def build_groups(blockers_np, group_ids):
                              else np.zeros(0, dt))
     bin_items = cat(item_parts, np.int32)
     strips = np.concatenate(strip_parts + [np.zeros((1, 2))])           # never empty
+    group_of = np.full(len(ids), -1, np.int32)
+    for g, (idx, _) in enumerate(member_lists):
+        group_of[idx] = g
     return (groups, cat(members, np.int32), cat(ptr_parts, np.int32),
             bin_items if len(bin_items) else np.zeros(1, np.int32),
-            np.ascontiguousarray(strips, dtype=np.float64))
+            np.ascontiguousarray(strips, dtype=np.float64), group_of)
 
 
 def make_blockers_host(surf_points, surf_normals):
@@ -390,19 +394,31 @@ def make_blockers_host(surf_points, surf_normals):
     return out
 
 
-def visibility_p2p_grouped_host(centers, surf_normals, surf_points, group_ids):
-    """CPU twin of the grouped visibility kernel (numpy) -- tests only."""
+def _own_group(group_of, n):
+    """Per centre i the group of blocker i (-1 where there is no blocker i)."""
+    import numpy as np
+    out = np.full(n, -1, np.int32)
+    k = min(n, len(group_of))
+    out[:k] = group_of[:k]
+    return out
+
+
+def visibility_p2p_grouped_host(centers, surf_normals, surf_points, group_ids, hints=True):
+    """CPU twin of the grouped visibility kernel (numpy) -- tests only.  ``hints=False``
+    switches the memoised own-polygon test and the own-walls-first order off."""
     import numpy as np
     lib = _lib.load()
     cen = np.ascontiguousarray(centers, dtype=np.float64)
     blk = make_blockers_host(surf_points, surf_normals)
-    groups, members, bin_ptr, bin_items, strips = build_groups(blk, group_ids)
+    groups, members, bin_ptr, bin_items, strips, group_of = build_groups(blk, group_ids)
     n = cen.shape[0]
+    own_group = _own_group(group_of, n)
     vis = np.zeros((n, n), np.uint8)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
-    rc = lib.spb_visibility_p2p_grouped_host(p(cen), ctypes.c_int64(n), p(blk), p(groups),
-                                             ctypes.c_int64(len(groups)), p(members),
-                                             p(bin_ptr), p(bin_items), p(strips), p(vis))
+    rc = lib.spb_visibility_p2p_grouped_host(
+        p(cen), ctypes.c_int64(n), p(blk), p(groups), ctypes.c_int64(len(groups)), p(members),
+        p(bin_ptr), p(bin_items), p(strips), ctypes.c_int64(min(n, len(blk)) if hints else 0),
+        p(own_group) if hints else None, p(vis))
     assert rc == 0
     return vis.astype(bool)
 
@@ -417,19 +433,25 @@ def visibility_p2p_grouped(centers, surf_normals, surf_points, group_ids, row_ra
     blockers = make_blockers(surf_points, surf_normals)
     m = surf_points.shape[0]
     blk_np = blockers.cpu().numpy().reshape(m, -1)
-    groups, members, bin_ptr, bin_items, strips = build_groups(
+    groups, members, bin_ptr, bin_items, strips, group_of = build_groups(
         blk_np, group_ids.cpu().numpy() if isinstance(group_ids, torch.Tensor) else group_ids)
     dev = centers.device
     t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    # memo "centre i lies in polygon i" and the group of blocker i (result-neutral hints)
+    own_in = torch.full((n,), 255, dtype=torch.uint8, device=dev)
+    _lib.call("spb_visibility_own_in", centers, min(n, m), blockers, own_in, _lib.stream_ptr())
+    own_group = t(_own_group(group_of, n))
     if row_range is None:
         vis = torch.empty((n, n), dtype=torch.uint8, device=dev)
         _lib.call("spb_visibility_p2p_grouped", centers, n, blockers, t(groups), len(groups),
-                  t(members), t(bin_ptr), t(bin_items), t(strips), vis, _lib.stream_ptr())
+                  t(members), t(bin_ptr), t(bin_items), t(strips), own_in, own_group, vis,
+                  _lib.stream_ptr())
         return vis.bool()
     lo, hi = int(row_range[0]), int(row_range[1])
     vis = torch.empty((hi - lo, n), dtype=torch.uint8, device=dev)
     _lib.call("spb_visibility_p2p_grouped_rows", centers, n, blockers, t(groups), len(groups),
-              t(members), t(bin_ptr), t(bin_items), t(strips), lo, hi, vis, _lib.stream_ptr())
+              t(members), t(bin_ptr), t(bin_items), t(strips), own_in, own_group, lo, hi, vis,
+              _lib.stream_ptr())
     return vis.bool()
 
 

@@ -9,6 +9,8 @@
 // form_factor/universal.py:12-160 + integration.py:38-344 (form factors, point
 // factors), RadiosityFast.py:403-414, :988-1034, :1277-1312, :1359-1390 (BRDF
 // direction indices, directional source energy).
+#include <vector>
+
 #include "common.cuh"
 #include "exact.cuh"
 #include "vis_group.cuh"
@@ -200,6 +202,13 @@ k_vis_pt2p(const double *__restrict__ points, const double *__restrict__ centers
 // (vis_group.cuh); the group headers are staged in shared memory when they fit
 constexpr int kMaxGroupsSmem = 128;
 
+// memo for the grouped kernel: is centre i inside polygon i (vis_group.cuh, exact::Own)
+__global__ void k_own_in(const double *__restrict__ centers, int64_t count,
+                         const Blocker *__restrict__ blockers, uint8_t *__restrict__ own_in) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) own_in[i] = exact::own_in_polygon(centers + 3 * i, blockers[i]) ? 1 : 0;
+}
+
 // 4 resident CTAs per SM (128 registers, 268 bytes of spills): measured 79.4 ms against
 // 92.3 ms with the 167 registers ptxas takes unbounded (C4, profiles/r02_sweep_vis_c4.jsonl)
 __global__ void __launch_bounds__(kVisThreads, 4)
@@ -207,7 +216,8 @@ k_vis_p2p_grouped(const double *__restrict__ centers, int64_t n,
                   const Blocker *__restrict__ blockers, const exact::Group *__restrict__ groups,
                   int32_t n_groups, const int32_t *__restrict__ members,
                   const int32_t *__restrict__ bin_ptr, const int32_t *__restrict__ bin_items,
-                  const double *__restrict__ strips, int64_t chunks_per_row, int64_t row_lo,
+                  const double *__restrict__ strips, const uint8_t *__restrict__ own_in,
+                  const int32_t *__restrict__ own_group, int64_t chunks_per_row, int64_t row_lo,
                   uint8_t *__restrict__ vis) {
     // rows [row_lo, row_lo + gridDim.x / chunks_per_row) of the matrix; vis holds those rows
     __shared__ exact::Group sg[kMaxGroupsSmem];
@@ -230,11 +240,18 @@ k_vis_p2p_grouped(const double *__restrict__ centers, int64_t n,
     const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
     const double vlen = sqrt(vv);
     const bool cull_ok = vv > 1e-6;
+    // the conjunction over the groups does not depend on their order: the walls the two
+    // patches lie on come first (they decide most invisible pairs: same wall, or the other
+    // patch behind this one's wall), with the memoised "centre in its own polygon" values
+    const exact::Own own = exact::make_own(i, j, own_in);
+    const int32_t g_a = own_group ? own_group[i] : -1, g_b = own_group ? own_group[j] : -1;
     bool visible = true;
-    for (int32_t g = 0; g < n_groups && visible; ++g) {
+    for (int32_t step = -2; step < n_groups && visible; ++step) {      // one call site
+        const int32_t g = step == -2 ? g_a : (step == -1 ? g_b : step);
+        if (g < 0 || (step >= -1 && g == g_a) || (step >= 0 && g == g_b)) continue;
         const exact::Group &grp = staged ? sg[g] : groups[g];
         visible = !exact::group_blocked(A, B, v, vlen, cull_ok, grp, blockers, members, bin_ptr,
-                                        bin_items, strips);
+                                        bin_items, strips, own);
     }
     vis[(i - row_lo) * n + j] = visible ? 1 : 0;
 }
@@ -666,11 +683,12 @@ using namespace spb;
 static int launch_vis_grouped(unsigned grid, cudaStream_t st, const double *centers, int64_t n,
                               const void *blockers, const void *groups, int64_t n_groups,
                               const int32_t *members, const int32_t *bin_ptr,
-                              const int32_t *bin_items, const double *strips, int64_t chunks,
+                              const int32_t *bin_items, const double *strips,
+                              const uint8_t *own_in, const int32_t *own_group, int64_t chunks,
                               int64_t row_lo, uint8_t *vis) {
     k_vis_p2p_grouped<<<grid, kVisThreads, 0, st>>>(
         centers, n, (const Blocker *)blockers, (const exact::Group *)groups, (int32_t)n_groups,
-        members, bin_ptr, bin_items, strips, chunks, row_lo, vis);
+        members, bin_ptr, bin_items, strips, own_in, own_group, chunks, row_lo, vis);
     return check_launch("k_vis_p2p_grouped");
 }
 
@@ -704,7 +722,8 @@ int spb_visibility_p2p(const double *centers, int64_t n, const void *blockers, i
 int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blockers,
                                const void *groups, int64_t n_groups, const int32_t *members,
                                const int32_t *bin_ptr, const int32_t *bin_items,
-                               const double *strips, uint8_t *vis, void *stream) {
+                               const double *strips, const uint8_t *own_in,
+                               const int32_t *own_group, uint8_t *vis, void *stream) {
     SPB_REQUIRE(centers && vis && blockers && groups && members && bin_ptr && bin_items &&
                 strips, "null pointer");
     SPB_REQUIRE(n_groups >= 0 && n_groups <= 2147483647LL, "n_groups");
@@ -714,13 +733,15 @@ int spb_visibility_p2p_grouped(const double *centers, int64_t n, const void *blo
     const int64_t chunks = ceil_div(n, kVisThreads);
     SPB_REQUIRE(n * chunks <= 2147483647LL, "too many patches for one launch");
     return launch_vis_grouped((unsigned)(n * chunks), st, centers, n, blockers, groups, n_groups,
-                              members, bin_ptr, bin_items, strips, chunks, 0, vis);
+                              members, bin_ptr, bin_items, strips, own_in, own_group, chunks, 0,
+                              vis);
 }
 
 int spb_visibility_p2p_grouped_rows(const double *centers, int64_t n, const void *blockers,
                                     const void *groups, int64_t n_groups,
                                     const int32_t *members, const int32_t *bin_ptr,
                                     const int32_t *bin_items, const double *strips,
+                                    const uint8_t *own_in, const int32_t *own_group,
                                     int64_t row_lo, int64_t row_hi, uint8_t *vis_rows,
                                     void *stream) {
     SPB_REQUIRE(centers && vis_rows && blockers && groups && members && bin_ptr && bin_items &&
@@ -734,8 +755,17 @@ int spb_visibility_p2p_grouped_rows(const double *centers, int64_t n, const void
     const int64_t chunks = ceil_div(n, kVisThreads);
     SPB_REQUIRE(rows * chunks <= 2147483647LL, "too many rows for one launch");
     return launch_vis_grouped((unsigned)(rows * chunks), st, centers, n, blockers, groups,
-                              n_groups, members, bin_ptr, bin_items, strips, chunks, row_lo,
-                              vis_rows);
+                              n_groups, members, bin_ptr, bin_items, strips, own_in, own_group,
+                              chunks, row_lo, vis_rows);
+}
+
+int spb_visibility_own_in(const double *centers, int64_t count, const void *blockers,
+                          uint8_t *own_in, void *stream) {
+    SPB_REQUIRE(centers && blockers && own_in, "null pointer");
+    if (count == 0) return 0;
+    k_own_in<<<(unsigned)ceil_div(count, 128), 128, 0, (cudaStream_t)stream>>>(
+        centers, count, (const Blocker *)blockers, own_in);
+    return check_launch("k_own_in");
 }
 
 size_t spb_group_bytes(void) { return sizeof(exact::Group); }
@@ -756,8 +786,13 @@ int spb_visibility_p2p_grouped_host(const double *centers_h, int64_t n, const vo
                                     const void *groups_h, int64_t n_groups,
                                     const int32_t *members_h, const int32_t *bin_ptr_h,
                                     const int32_t *bin_items_h, const double *strips_h,
-                                    uint8_t *vis_h) {
+                                    int64_t n_own, const int32_t *own_group_h, uint8_t *vis_h) {
     SPB_REQUIRE(centers_h && vis_h && blockers_h && groups_h && strips_h, "null pointer");
+    SPB_REQUIRE(n_own >= 0 && n_own <= n, "n_own");
+    // memo of the first n_own centres (centre i <-> blocker i), 255 = not computed
+    std::vector<uint8_t> own_in((size_t)n, 255);
+    for (int64_t i = 0; i < n_own; ++i)
+        own_in[i] = exact::own_in_polygon(centers_h + 3 * i, ((const Blocker *)blockers_h)[i]);
     const Blocker *blockers = (const Blocker *)blockers_h;
     const exact::Group *groups = (const exact::Group *)groups_h;
     for (int64_t i = 0; i < n; ++i)
@@ -768,11 +803,17 @@ int spb_visibility_p2p_grouped_host(const double *centers_h, int64_t n, const vo
                 double v[3];
                 exact::sub3(B, A, v);
                 const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+                const exact::Own own = exact::make_own(i, j, n_own ? own_in.data() : nullptr);
+                const int64_t g_a = own_group_h ? own_group_h[i] : -1;
+                const int64_t g_b = own_group_h ? own_group_h[j] : -1;
                 bool visible = true;
-                for (int64_t g = 0; g < n_groups && visible; ++g)
+                for (int64_t step = -2; step < n_groups && visible; ++step) {
+                    const int64_t g = step == -2 ? g_a : (step == -1 ? g_b : step);
+                    if (g < 0 || (step >= -1 && g == g_a) || (step >= 0 && g == g_b)) continue;
                     visible = !exact::group_blocked(A, B, v, sqrt(vv), vv > 1e-6, groups[g],
                                                     blockers, members_h, bin_ptr_h, bin_items_h,
-                                                    strips_h);
+                                                    strips_h, own);
+                }
                 out = visible ? 1 : 0;
             }
             vis_h[i * n + j] = out;

@@ -231,8 +231,12 @@ SPB_FN bool point_in_polygon(const double *p, const Blocker &k) {
 //        E -+ (dE/dp) v, at most eta*|v|/|dp| away from E.  If ray_clearance(E)
 //        exceeds that distance (+3e-9 for rounding), "hit in polygon" is False.
 //    v = B - A, vlen = |v| (any rounding), cull_ok = |v|^2 > 1e-6.
+//    hint_a / hint_b: value of point_in_polygon_sides for the in-plane coordinates of A / B
+//    with THIS blocker when it was computed before (0 / 1; -1 = not known) -- the function is
+//    pure, so a memoised value is the value; see own_in in vis_group.cuh.
 SPB_FN bool blocked(const double *A, const double *B, const double *v,
-                                        double vlen, bool cull_ok, const Blocker &k) {
+                                        double vlen, bool cull_ok, const Blocker &k,
+                                        int hint_a = -1, int hint_b = -1) {
     double wa[3], w[3];
     sub3(A, k.s0, wa);
     sub3(B, k.s0, w);
@@ -247,13 +251,15 @@ SPB_FN bool blocked(const double *A, const double *B, const double *v,
         if (copA) {
             const double ax = dot3(k.r0, A), ay = dot3(k.r1, A);
             const double clr = ray_clearance(ax, ay, k);
-            if (!(clr > kClearGuard)) inA = point_in_polygon_sides(ax, ay, &k);
+            if (!(clr > kClearGuard))
+                inA = hint_a >= 0 ? hint_a != 0 : point_in_polygon_sides(ax, ay, &k);
             else if (!copB) hit_misses = clr > slack;
         }
         if (copB) {
             const double bx = dot3(k.r0, B), by = dot3(k.r1, B);
             const double clr = ray_clearance(bx, by, k);
-            if (!(clr > kClearGuard)) inB = point_in_polygon_sides(bx, by, &k);
+            if (!(clr > kClearGuard))
+                inB = hint_b >= 0 ? hint_b != 0 : point_in_polygon_sides(bx, by, &k);
             else if (!copA) hit_misses = clr > slack;
         }
     }

@@ -56,12 +56,38 @@ struct Group {
 
 constexpr double kGroupMargin = 1e-3;    // how far a member's hit may differ from the group's
 
+// Memo of the one exact polygon test almost every pair needs twice: an end point that is the
+// centre of a patch lies in that patch's own plane and polygon, so the member with the end
+// point's own index always reaches point_in_polygon_sides (x87-emulated norms, ~1000
+// instructions).  own_in[i] = point_in_polygon_sides(centre i in the frame of blocker i) is
+// computed once per patch (own_in_polygon below) and handed to exact::blocked as a hint when
+// the member's index equals the end point's index.  255 = not computed.
+struct Own {
+    int32_t a, b;        // index of end point A / B (= index of "its" blocker), -1: none
+    int a_in, b_in;      // memoised point_in_polygon_sides, -1: not known
+};
+SPB_FN Own no_own() { return Own{-1, -1, -1, -1}; }
+SPB_FN Own make_own(int64_t i, int64_t j, const uint8_t *own_in) {
+    if (!own_in) return no_own();
+    const int ai = own_in[i], bi = own_in[j];
+    return Own{(int32_t)i, (int32_t)j, ai <= 1 ? ai : -1, bi <= 1 ? bi : -1};
+}
+SPB_FN bool own_in_polygon(const double *c, const Blocker &k) {
+    return point_in_polygon_sides(dot3(k.r0, c), dot3(k.r1, c), &k);   // as in exact::blocked
+}
+SPB_FN bool blocked_member(const double *A, const double *B, const double *v, double vlen,
+                           bool cull_ok, const Blocker *blockers, int32_t m, const Own &own) {
+    return blocked(A, B, v, vlen, cull_ok, blockers[m], m == own.a ? own.a_in : -1,
+                   m == own.b ? own.b_in : -1);
+}
+
 // every member of the group, one by one (always correct)
 SPB_FN bool group_blocked_bruteforce(const double *A, const double *B, const double *v,
                                      double vlen, bool cull_ok, const Group &g,
-                                     const Blocker *blockers, const int32_t *members) {
+                                     const Blocker *blockers, const int32_t *members,
+                                     const Own &own) {
     for (int32_t q = g.m0; q < g.m1; ++q)
-        if (blocked(A, B, v, vlen, cull_ok, blockers[members[q]])) return true;
+        if (blocked_member(A, B, v, vlen, cull_ok, blockers, members[q], own)) return true;
     return false;
 }
 
@@ -81,7 +107,7 @@ SPB_FN bool in_strip(const Group &g, int32_t bin, double qy, const int32_t *bin_
 SPB_FN bool group_blocked_near(const double *A, const double *B, const double *v, double vlen,
                                bool cull_ok, const Group &g, double qx, double qy,
                                const Blocker *blockers, const int32_t *bin_ptr,
-                               const int32_t *bin_items, const double *strips) {
+                               const int32_t *bin_items, const double *strips, const Own &own) {
     const double fb = (qy - g.y0) * g.inv_bin_h;
     if (!(fb > -1.0) || !(fb < (double)g.n_bins + 1.0)) return false;   // outside every band
     int32_t bin = (int32_t)floor(fb);
@@ -94,9 +120,9 @@ SPB_FN bool group_blocked_near(const double *A, const double *B, const double *v
     }
     const int32_t p0 = bin_ptr[list], p1 = bin_ptr[list + 1];
     for (int32_t p = p0; p < p1; ++p) {
-        const Blocker &k = blockers[bin_items[p]];
-        if (ray_clearance(qx, qy, k) > kGroupMargin + kClearGuard) continue;
-        if (blocked(A, B, v, vlen, cull_ok, k)) return true;
+        const int32_t m = bin_items[p];
+        if (ray_clearance(qx, qy, blockers[m]) > kGroupMargin + kClearGuard) continue;
+        if (blocked_member(A, B, v, vlen, cull_ok, blockers, m, own)) return true;
     }
     return false;
 }
@@ -105,7 +131,7 @@ SPB_FN bool group_blocked_near(const double *A, const double *B, const double *v
 SPB_FN bool group_blocked(const double *A, const double *B, const double *v, double vlen,
                           bool cull_ok, const Group &g, const Blocker *blockers,
                           const int32_t *members, const int32_t *bin_ptr,
-                          const int32_t *bin_items, const double *strips) {
+                          const int32_t *bin_items, const double *strips, const Own &own) {
     double wa[3], w[3];
     sub3(A, g.s0, wa);
     sub3(B, g.s0, w);
@@ -116,7 +142,7 @@ SPB_FN bool group_blocked(const double *A, const double *B, const double *v, dou
     const bool offA = fabs(dA) > kEta + dev, offB = fabs(dB) > kEta + dev;
     const bool inplA = fabs(dA) < kEta - dev, inplB = fabs(dB) < kEta - dev;
     if (!(offA || inplA) || !(offB || inplB) || !cull_ok || !(vlen < 1e4))
-        return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
+        return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members, own);
 
     if (offA && offB) {
         // neither end point lies in any member's plane
@@ -128,23 +154,23 @@ SPB_FN bool group_blocked(const double *A, const double *B, const double *v, dou
         if (outside) return false;
         const double shift = dev * vlen / fabs(dp) + 1e-9;          // |hit_k - hit_group|
         if (!(shift < kGroupMargin))
-            return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
+            return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members, own);
         const double fac = -(dB / dp);
         const double pt[3] = {(w[0] + g.s0[0]) + fac * v[0], (w[1] + g.s0[1]) + fac * v[1],
                               (w[2] + g.s0[2]) + fac * v[2]};
         return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, pt), dot3(g.r1, pt),
-                                  blockers, bin_ptr, bin_items, strips);
+                                  blockers, bin_ptr, bin_items, strips, own);
     }
     if (inplA && inplB) {
         // both end points in the plane: a member blocks only if an end point is in its
         // polygon -- unless there is a "plane hit" with |dp| > 1e-6 (dp ~ dB - dA <= 2e-6)
         if (fabs(dp) > 1e-6)
-            return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
+            return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members, own);
         if (group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, A), dot3(g.r1, A), blockers,
-                               bin_ptr, bin_items, strips))
+                               bin_ptr, bin_items, strips, own))
             return true;
         return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, B), dot3(g.r1, B),
-                                  blockers, bin_ptr, bin_items, strips);
+                                  blockers, bin_ptr, bin_items, strips, own);
     }
     // exactly one end point E in the plane, the other clearly off it: a member blocks
     // only if E is in its polygon, or the plane hit -- within eta*|v|/|dp| of E -- is
@@ -153,14 +179,14 @@ SPB_FN bool group_blocked(const double *A, const double *B, const double *v, dou
         // no plane hit: only "E in the polygon" can block
         const double *E = inplA ? A : B;
         return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, E), dot3(g.r1, E),
-                                  blockers, bin_ptr, bin_items, strips);
+                                  blockers, bin_ptr, bin_items, strips, own);
     }
     const double slack = (kEta + dev) * vlen / fabs(dp) + 3e-9;
     if (!(slack < kGroupMargin))
-        return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members);
+        return group_blocked_bruteforce(A, B, v, vlen, cull_ok, g, blockers, members, own);
     const double *E = inplA ? A : B;
     return group_blocked_near(A, B, v, vlen, cull_ok, g, dot3(g.r0, E), dot3(g.r1, E), blockers,
-                              bin_ptr, bin_items, strips);
+                              bin_ptr, bin_items, strips, own);
 }
 
 }  // namespace exact

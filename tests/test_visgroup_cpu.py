@@ -9,8 +9,12 @@ from conftest import load_golden
 
 
 def grouped(oracle, cen, nrm, pts, ids):
+    """Grouped visibility with the result-neutral hints (memoised own-polygon test, own walls
+    first) -- checked here to BE result-neutral -- and the oracle's matrix."""
     from sparrowpy_b200 import bake
     vis = bake.visibility_p2p_grouped_host(cen, nrm, pts, ids)
+    plain = bake.visibility_p2p_grouped_host(cen, nrm, pts, ids, hints=False)
+    assert np.array_equal(vis, plain)
     ref = oracle.visibility_p2p(cen, nrm, pts)
     return vis, ref
 
@@ -49,7 +53,7 @@ def test_group_table_layout():
     pts, ids = geometry.process_patches(wp, 0.5)
     blk = bake.make_blockers_host(pts, wn[ids])
     assert blk.shape == (len(ids), 38) and (blk[:, 37] == 1.0).all()      # all axis-aligned
-    groups, members, bin_ptr, bin_items, strips = bake.build_groups(blk, ids)
+    groups, members, bin_ptr, bin_items, strips, group_of = bake.build_groups(blk, ids)
     assert len(groups) == 6 and sorted(members.tolist()) == list(range(len(ids)))
     gi = groups.view(np.int32).reshape(6, -1)
     I = bake._GRP_I
@@ -149,7 +153,7 @@ def test_cells_equal_bins_on_the_street_canyon():
     pts, ids = geometry.process_patches(wp, 1.0)
     cen = geometry.calculate_center(pts)
     blk = bake.make_blockers_host(pts, wn[ids])
-    groups, members, bin_ptr, bin_items, strips = bake.build_groups(blk, ids)
+    groups, members, bin_ptr, bin_items, strips, group_of = bake.build_groups(blk, ids)
     gi = groups.view(np.int32).reshape(len(groups), -1)
     assert (gi[:, bake._GRP_I["n_bx"]] > 0).all()
     sel = np.sort(np.random.default_rng(3).choice(len(cen), 700, replace=False))
@@ -161,7 +165,8 @@ def test_cells_equal_bins_on_the_street_canyon():
         vis = np.zeros((len(c), len(c)), np.uint8)
         assert lib.spb_visibility_p2p_grouped_host(
             p(c), ctypes.c_int64(len(c)), p(blk), p(table), ctypes.c_int64(len(table)),
-            p(members), p(bin_ptr), p(bin_items), p(strips), p(vis)) == 0
+            p(members), p(bin_ptr), p(bin_items), p(strips), ctypes.c_int64(0), None,
+            p(vis)) == 0
         return vis
 
     no_cells = groups.copy()

@@ -31,7 +31,10 @@ def main():
     off = tabs[0].copy()
     off.view(np.int32).reshape(len(off), -1)[:, bake._GRP_I["n_bx"]] = 0
     ref = None
-    for name, groups in (("cells", tabs[0]), ("bins only", off)):
+    own_in = torch.full((n,), 255, dtype=torch.uint8, device=dev)
+    _lib.call("spb_visibility_own_in", g["center"], n, blockers, own_in, _lib.stream_ptr())
+    for name, groups, hints in (("cells + own-patch memo + own walls first", tabs[0], True),
+                                ("cells", tabs[0], False), ("bins only", off, False)):
         dv = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (groups,) + tabs[1:]]
         vis = torch.empty((n, n), dtype=torch.uint8, device=dev)
         ms = []
@@ -39,7 +42,8 @@ def main():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             ev[0].record()
             _lib.call("spb_visibility_p2p_grouped", g["center"], n, blockers, dv[0], len(groups),
-                      dv[1], dv[2], dv[3], dv[4], vis, _lib.stream_ptr())
+                      dv[1], dv[2], dv[3], dv[4], own_in if hints else None,
+                      dv[5] if hints else None, vis, _lib.stream_ptr())
             ev[1].record()
             torch.cuda.synchronize()
             ms.append(ev[0].elapsed_time(ev[1]))
@@ -49,6 +53,23 @@ def main():
                           "ms": [round(x, 2) for x in ms],
                           "visible_pairs": int(vis.sum().item()),
                           "equals_first": bool(torch.equal(vis, ref))}), flush=True)
+    time_form_factors(g, ref, args.reps)
+
+
+def time_form_factors(g, vis, reps=2):
+    """Stokes / Nusselt form factors of the visible pairs (k_ff_stokes, k_ff_nusselt)."""
+    from sparrowpy_b200 import bake
+    pairs = torch.nonzero(vis).to(torch.int32).contiguous()
+    ms = []
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        bake.form_factors(g["points"], g["normal"], g["area"], pairs)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms.append(ev[0].elapsed_time(ev[1]))
+    print(json.dumps({"form_factors_ms": [round(x, 2) for x in ms],
+                      "pairs": int(pairs.shape[0])}), flush=True)
 
 
 if __name__ == "__main__":

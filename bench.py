@@ -835,7 +835,8 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
             "bound": "lsu" if staged else "hbm",
             "kernel": "k_collect_staged" if staged else "k_collect_partial",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None,
+            "traffic": c3_traffic("k_collect_staged" if staged else "k_collect_partial",
+                                  args.dtype, world),
             "peak_source": ("128 B/clk/SM shared-memory operand path x 148 SMs x the SM clock "
                             "sampled in the timed region" if staged
                             else "measured (MEASURED_PEAKS.json hbm_gbs)"),
@@ -849,7 +850,7 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
             "note": "algorithmic bytes = one histogram element per (source, receiver, patch, "
                     "band, bin) contribution (SURVEY 8d); the staged kernel reads each of them "
                     "from shared memory (the row of a (source, patch) is fetched once per "
-                    "group of 16 receivers), so the operand path, not HBM, is the roof"}
+                    "group of 8 receivers), so the operand path, not HBM, is the roof"}
         line = {
             "metric": "source*receiver*patch*band*bin contributions/s (order-0 ETCs at all "
                       "receivers; BASELINE config 3)",
@@ -880,6 +881,18 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def c3_traffic(kernel, dtype, world):
+    """DRAM bytes per launch of the collection kernel from the ncu capture under profiles/
+    (1 GPU, all receivers), None when there is none."""
+    if world > 1:
+        return None
+    try:
+        tr = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+        return tr.get(f"c3/{dtype}/{kernel}", {}).get("bytes")
+    except OSError:
+        return None
 
 
 def cpu_c3_rate(rad, cfg, srcs, rcvs, log, budget_s=15.0):

@@ -220,16 +220,15 @@ int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *sh
 
 /* The same sum for MANY receivers of a diffuse scene (n_dirs = 1, so `rdir` is all zeros and
  * is not passed): every histogram row is staged once in shared memory and applied to a group
- * of receivers from there (k_collect_staged) instead of being re-read per receiver -- the
- * reference loops over the receivers in Python (RadiosityFast.py:711).  shape: receivers x bins
- * per thread, 0 = auto (8x4), 1 = 16x4, 2 = 8x4, 3 = 8x8; n_stages: depth of the cp.async ring,
- * 0 = auto, else 2..4.  Fails (-1) when a row does not fit shared memory; `partial` and the
- * result layout are those of spb_collect_mono. */
+ * of 8 receivers from there (k_collect_staged) instead of being re-read per receiver -- the
+ * reference loops over the receivers in Python (RadiosityFast.py:711).  n_stages: depth of the
+ * cp.async ring, 0 = auto, else 2..4.  Fails (-1) when a row does not fit shared memory;
+ * `partial` and the result layout are those of spb_collect_mono. */
 int spb_collect_mono_staged(const void *e_total, const int32_t *shift, const void *scale,
                             int64_t n_receivers, int64_t n_patches, int64_t n_alloc,
                             int64_t n_bands, int64_t n_samples, int64_t ld, int64_t pad,
-                            void *mono, void *partial, int64_t n_split, int shape,
-                            int n_stages, int dtype, void *stream);
+                            void *mono, void *partial, int64_t n_split, int n_stages,
+                            int dtype, void *stream);
 
 /* patch-wise variant (`collect_energy_receiver_patchwise`, RadiosityFast.py:660):
  * out: [R, N, B, T] dense. */

@@ -724,30 +724,23 @@ int spb_collect_mono(const void *e_total, const int32_t *rdir, const int32_t *sh
 int spb_collect_mono_staged(const void *e_total, const int32_t *shift, const void *scale,
                             int64_t n_receivers, int64_t n_patches, int64_t n_alloc,
                             int64_t n_bands, int64_t n_samples, int64_t ld, int64_t pad,
-                            void *mono, void *partial, int64_t n_split, int shape,
-                            int n_stages, int dtype, void *stream) {
+                            void *mono, void *partial, int64_t n_split, int n_stages,
+                            int dtype, void *stream) {
     SPB_REQUIRE(e_total && shift && scale && mono && partial, "null pointer");
     SPB_REQUIRE(n_split >= 1 && n_split <= 65535, "n_split");
     SPB_REQUIRE(n_samples >= 1 && n_samples < (1 << 30), "n_samples");
     SPB_REQUIRE(dtype == SPB_F64 || dtype == SPB_F32, "dtype");
     if (n_receivers == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (shape == 0) shape = 2;
-#define SPB_STAGED(T, R, Q)                                                                 \
-    return collect_staged_t<T, R, Q>(e_total, shift, scale, n_receivers, n_patches, n_alloc, \
-                                     n_bands, n_samples, ld, pad, mono, partial, n_split,    \
-                                     n_stages, st)
-    if (dtype == SPB_F64) {
-        if (shape == 1) SPB_STAGED(double, 16, 4);
-        if (shape == 2) SPB_STAGED(double, 8, 4);
-        if (shape == 3) SPB_STAGED(double, 8, 8);
-    } else {
-        if (shape == 1) SPB_STAGED(float, 16, 4);
-        if (shape == 2) SPB_STAGED(float, 8, 4);
-        if (shape == 3) SPB_STAGED(float, 8, 8);
-    }
-#undef SPB_STAGED
-    return fail(-1, "invalid argument", "shape must be 0 (auto), 1 (16x4), 2 (8x4) or 3 (8x8)");
+    // 8 receivers x 4 bins per thread, two CTAs per SM: the fastest of the shapes measured
+    // (16x4, 8x8, two sets of 8x4 in a 512-thread CTA: profiles/r02_sweep_collect_*.jsonl)
+    if (dtype == SPB_F64)
+        return collect_staged_t<double, 8, 4>(e_total, shift, scale, n_receivers, n_patches,
+                                              n_alloc, n_bands, n_samples, ld, pad, mono, partial,
+                                              n_split, n_stages, st);
+    return collect_staged_t<float, 8, 4>(e_total, shift, scale, n_receivers, n_patches, n_alloc,
+                                         n_bands, n_samples, ld, pad, mono, partial, n_split,
+                                         n_stages, st);
 }
 
 int spb_collect_patchwise(const void *e_total, const int32_t *rdir, const int32_t *shift,

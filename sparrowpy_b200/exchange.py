@@ -519,34 +519,31 @@ def _energy_exchange_batch(tables, e0, delay0, n_samples, max_order):
     return hist
 
 
-STAGED_SHAPES = {1: (16, 4), 2: (8, 4), 3: (8, 8)}    # receivers x bins per thread
+STAGED_RECEIVERS, STAGED_BINS = 8, 4     # per CTA / per thread (csrc/exchange.cu)
 
 
 def collect_kind(hist, n_rcv):
-    """Which collection kernel sums the patches: ``("staged", shape, stages)`` --
-    `k_collect_staged`, every histogram row staged once in shared memory for a group of
+    """Which collection kernel sums the patches: ``("staged", stages)`` --
+    `k_collect_staged`, every histogram row staged once in shared memory for a group of 8
     receivers (diffuse scenes with many receivers, BASELINE config 3) -- or ``("direct",)``,
     `k_collect_partial` (one row read per receiver).  ``SPB_COLLECT=direct`` or
-    ``staged[:shape[:stages]]`` forces one (cross-check tests, tools/sweep_collect.py)."""
+    ``staged[:stages]`` forces one (cross-check tests, tools/sweep_collect.py)."""
     env = os.environ.get("SPB_COLLECT", "").split(":")
     esize = hist.data.element_size()
-    shape = 2           # 8 receivers x 4 bins, 2 CTAs per SM: fastest at T = 1000 and 2000
-    stages = 0
-    if env[0] == "staged":
-        shape = int(env[1]) if len(env) > 1 else shape
-        stages = int(env[2]) if len(env) > 2 else 0
-    n_r, n_q = STAGED_SHAPES[shape]
+    stages = int(env[1]) if env[0] == "staged" and len(env) > 1 else 0
     vec = 16 // esize
-    row2 = -(-hist.n_samples // vec) * vec + -(-hist.n_samples // (256 * n_q)) * 256 * n_q
-    fits = hist.n_dirs == 1 and max(2, stages) * ((row2 + n_r) * esize + 4 * n_r) <= 220 * 1024
+    chunk = 256 * STAGED_BINS
+    row2 = -(-hist.n_samples // vec) * vec + -(-hist.n_samples // chunk) * chunk
+    stage_bytes = (row2 + STAGED_RECEIVERS) * esize + 4 * STAGED_RECEIVERS
+    fits = hist.n_dirs == 1 and max(2, stages) * stage_bytes <= 220 * 1024
     if env[0] == "staged":
         if not fits:
             raise _lib.SparrowB200Error("SPB_COLLECT=staged needs one direction per patch and "
                                         "histogram rows that fit shared memory")
-        return ("staged", shape, stages)
+        return ("staged", stages)
     if env[0] == "direct" or not fits or n_rcv < 4:
         return ("direct",)
-    return ("staged", shape, stages)
+    return ("staged", stages)
 
 
 def collect_mono(hist, rdir, shift, scale, n_split=None):
@@ -565,8 +562,8 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
     if n_split is None:
         n_split = max(1, min(64, hist.n_patches // 256))
         if kind[0] == "staged":             # ~8 waves of CTAs (2 per SM), >= 64 patches each
-            n_r, n_q = STAGED_SHAPES[kind[1]]
-            ctas = hist.n_bands * -(-n_rcv // n_r) * -(-hist.n_samples // (256 * n_q))
+            ctas = (hist.n_bands * -(-n_rcv // STAGED_RECEIVERS)
+                    * -(-hist.n_samples // (256 * STAGED_BINS)))
             n_split = max(1, min(hist.n_patches // 64, -(-8 * 2 * 148 // ctas)))
     out = torch.empty((n_rcv, hist.n_bands, hist.n_samples), dtype=tdt,
                       device=hist.data.device)
@@ -580,8 +577,7 @@ def collect_mono(hist, rdir, shift, scale, n_split=None):
             _lib.call("spb_collect_mono_staged", hist.data, shift[r0:r1].contiguous(),
                       scale[r0:r1].to(tdt).contiguous(), r1 - r0, hist.n_patches, hist.n_alloc,
                       hist.n_bands, hist.n_samples, hist.ld, hist.pad, out[r0:r1], partial,
-                      n_split, _lib.I32(kind[1]), _lib.I32(kind[2]), _lib.I32(code),
-                      _lib.stream_ptr())
+                      n_split, _lib.I32(kind[1]), _lib.I32(code), _lib.stream_ptr())
             continue
         _lib.call("spb_collect_mono", hist.data, rdir[r0:r1].contiguous(),
                   shift[r0:r1].contiguous(), scale[r0:r1].to(tdt).contiguous(), r1 - r0,

@@ -1,5 +1,6 @@
 """Time the receiver-collection kernels on a config-3-sized histogram (random data):
-`k_collect_partial` (direct) against the shapes / ring depths of `k_collect_staged`.
+`k_collect_partial` (direct) against the ring depths of `k_collect_staged` (the shapes that
+were measured -- 16x4, 8x8, 512-thread CTAs -- are recorded under profiles/r02_sweep_collect_*).
 
     python tools/sweep_collect.py [--bands 16 --patches 40000 --samples 1000 --receivers 64]
 
@@ -22,8 +23,7 @@ def main():
     ap.add_argument("--receivers", type=int, default=64)
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--variants", default="direct,staged:1:2,staged:1:3,staged:1:4,staged:2:2,"
-                    "staged:2:3,staged:2:4,staged:3:2,staged:3:3")
+    ap.add_argument("--variants", default="direct,staged:2,staged:3,staged:4")
     ap.add_argument("--splits", default="0,16,32")
     args = ap.parse_args()
     from sparrowpy_b200 import _lib, exchange

@@ -375,6 +375,25 @@ def measure_fma_peak(code, dev, reps=5):
 
 
 # ---------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its
+    version banner with printf when the first communicator is created): keep the real stdout
+    for `emit` and send file descriptor 1 -- C stdio included -- to stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,6 +413,7 @@ def main():
                          "needs to this .npz (used by --impl reference in a child process)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     cfg = CONFIGS[args.config]
     os.environ["SPB_GATHER"] = args.gather
     gather = "tma" if (args.gather == "tmem" and args.dtype != "f64") else args.gather
@@ -677,7 +697,7 @@ def main():
             line["pipeline"] = pipeline
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -878,7 +898,7 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -1101,7 +1121,7 @@ def run_large(args, cfg, rank, world, local_rank, warmup, log):
                              "all-to-all (distributed.sharded_bake_tables)"},
             "exchange_peak_memory_gb_rank0": torch.cuda.max_memory_allocated(dev) / 1e9,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -1127,7 +1147,7 @@ def run_reference(args, cfg, rank, world, log):
         srcs = grid_points(*cfg["sources_grid"], half)
         rcvs = grid_points(*cfg["receivers_grid"], half)
         res = cpu_c3_rate(rad, cfg, srcs, rcvs, log, budget_s=20.0)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "source*receiver*patch*band*bin contributions/s "
             "(order-0 ETCs at all receivers; BASELINE config 3)", "value": res["value"],
             "unit": "contributions/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -1136,7 +1156,7 @@ def run_reference(args, cfg, rank, world, log):
             "data": "synthetic", "config": {"workload": cfg["desc"], "name": args.config},
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": "contributions/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0}}), flush=True)
+                    "d2h_bytes_per_step": 0}})
         return
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, "baked.npz")
@@ -1147,8 +1167,8 @@ def run_reference(args, cfg, rank, world, log):
                                capture_output=True, text=True)
         if child.returncode != 0 or not os.path.exists(path):
             why = (child.stderr.strip().splitlines() or ["bake failed"])[-1][:200]
-            print(json.dumps({"impl": "reference",
-                              "unavailable": f"scene baking needs the CUDA path: {why}"}))
+            emit({"impl": "reference",
+                  "unavailable": f"scene baking needs the CUDA path: {why}"})
             return
         inp = dict(np.load(path))
     n_patches = int(inp["n_patches"])
@@ -1190,7 +1210,7 @@ def run_reference(args, cfg, rank, world, log):
                 "like figure; the scene's baked arrays are inputs, produced by a child process "
                 "(CUDA bake) -- this process never loads the CUDA library",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -63,5 +63,7 @@ def test_reference_arm_without_a_gpu_reports_unavailable():
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0, out.stderr[-500:]
-    line = json.loads(out.stdout.strip().splitlines()[-1])
+    lines = out.stdout.strip().splitlines()
+    assert len(lines) == 1, lines          # ONE JSON line on stdout, whatever libraries print
+    line = json.loads(lines[0])
     assert line["impl"] == "reference" and "CUDA" in line["unavailable"]

@@ -266,3 +266,32 @@ def test_window_records_encode_the_same_pairs(gather="tmem"):
     counts = (t.win_ptr[1:] - t.win_ptr[:-1]).numpy()
     batch = exchange.tmem_batch()
     assert np.all(counts % batch == 0) and n_null < batch * len(counts)
+
+
+def test_csr_lists_of_index_ranges():
+    """bake._csr_lists: element k is a member of the lists first[k]..last[k], order kept."""
+    from sparrowpy_b200 import bake
+    first, last = np.array([0, 2, 1, 3, 2]), np.array([1, 2, 3, 2, 2])     # element 3: empty range
+    ptr, items = bake._csr_lists(first, last, 5, np.array([10, 11, 12, 13, 14], np.int32))
+    lists = [items[ptr[i]:ptr[i + 1]].tolist() for i in range(5)]
+    assert lists == [[10], [10, 12], [11, 12, 14], [12], []]
+
+
+def test_collection_kernel_choice_is_host_logic(monkeypatch):
+    """exchange.collect_kind needs no device: staged for diffuse histograms with >= 4 receivers
+    whose doubled rows fit shared memory, direct otherwise; SPB_COLLECT overrides."""
+    import torch
+    from sparrowpy_b200 import exchange
+    monkeypatch.delenv("SPB_COLLECT", raising=False)
+    hist = exchange.EnergyHistogram(torch.zeros((4, 1056), dtype=torch.float64), 4, 1, 1, 1000, 32)
+    assert exchange.collect_kind(hist, 64) == ("staged", 0)
+    assert exchange.collect_kind(hist, 3) == ("direct",)
+    hist.n_samples = 13000                                   # 2 x (2 x 13000 + ...) x 8 B > 220 KB
+    assert exchange.collect_kind(hist, 64) == ("direct",)
+    hist.n_samples, hist.n_dirs = 1000, 16
+    assert exchange.collect_kind(hist, 64) == ("direct",)
+    hist.n_dirs = 1
+    monkeypatch.setenv("SPB_COLLECT", "direct")
+    assert exchange.collect_kind(hist, 64) == ("direct",)
+    monkeypatch.setenv("SPB_COLLECT", "staged:4")
+    assert exchange.collect_kind(hist, 1) == ("staged", 4)

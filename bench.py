@@ -803,11 +803,15 @@ def run_c3(args, cfg, rank, world, local_rank, warmup, log):
     with ClockSampler(local_rank) as clocks:
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        if os.environ.get("SPB_BENCH_PROFILE"):     # ncu --profile-from-start off: timed steps only
+            torch.cuda.profiler.start()
         ev_a.record(st)
         for _ in range(args.steps):
             mono = step()
         ev_b.record(st)
         barrier()
+        if os.environ.get("SPB_BENCH_PROFILE"):
+            torch.cuda.profiler.stop()
         elapsed_ms = ev_a.elapsed_time(ev_b)
     stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev.items()}
     if world > 1:

@@ -295,3 +295,33 @@ def test_collection_kernel_choice_is_host_logic(monkeypatch):
     assert exchange.collect_kind(hist, 64) == ("direct",)
     monkeypatch.setenv("SPB_COLLECT", "staged:4")
     assert exchange.collect_kind(hist, 1) == ("staged", 4)
+
+
+@pytest.mark.parametrize("esize", [8, 4])
+def test_doubled_row_addressing_of_the_staged_collection(esize):
+    """Model of k_collect_staged's shared-memory row (csrc/exchange.cu): copy A at
+    [t_al - T, t_al), copy B at [t_al, t_al + T), read at t_al - shift + t.  For every bin
+    t < T and shift in [0, T) that is E[(t - shift) mod T] -- the reference's np.roll
+    (RadiosityFast.py:1181-1183) -- and every thread of the CTA, tail threads included, stays
+    inside the stage."""
+    rng = np.random.default_rng(esize)
+    vec = 16 // esize
+    for n_samples in [1, 2, 3, 7, 64, 255, 256, 333, 1000, 1024, 1025, 2050]:
+        t_al = -(-n_samples // vec) * vec
+        n_chunks = -(-n_samples // 1024)
+        row_elems = n_chunks * 1024
+        row2 = t_al + row_elems
+        e = rng.uniform(1, 2, n_samples)
+        stage = np.full(row2, np.nan)
+        stage[2 * t_al:] = 0.0                         # zeroed once per stage
+        stage[t_al - n_samples:t_al] = e               # copy A
+        n_copy = min(t_al, row2 - t_al)                # 16-byte pieces of copy B (may spill)
+        stage[t_al:t_al + n_samples] = e
+        stage[t_al + n_samples:t_al + n_copy] = 7.0    # row padding carried along by the pieces
+        t_all = np.arange(row_elems)                   # chunk * 1024 + tid + 256 q
+        for shift in {0, 1, n_samples // 2, n_samples - 1}:
+            idx = t_al - shift + t_all
+            assert idx.min() >= 0 and idx.max() < row2
+            got = stage[idx[:n_samples]]
+            assert np.array_equal(got, np.roll(e, shift))
+            assert not np.isnan(stage[idx]).any()      # tail threads read initialised memory
